@@ -1,0 +1,354 @@
+"""ctypes binding of the C ABI (include/cna_b200.h) + NHWC tensor plumbing.
+
+torch is used for device memory and streams only.  Every compute call goes to
+lib/libcna_b200.so; there is no CPU path and no eager-PyTorch fallback: a missing
+library or a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_int, c_void_p
+
+import torch
+
+F32, BF16 = 0, 1
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libcna_b200.so")
+
+_lib = None
+
+# name -> argtypes ('p' pointer, 'i' int); all return int unless noted
+_SIGS = {
+    "cna_device_check": "",
+    "cna_nchw_to_nhwc": "ppiiiiiiip",
+    "cna_nhwc_to_nchw": "ppiiiiiiip",
+    "cna_pack_taps_weight": "ppiiiiiip",
+    "cna_pack_dw_weight": "ppiiiip",
+    "cna_conv_taps_forward": "pppppiiiiiiiiiiiip",
+    "cna_dwconv_forward": "ppppippiiiiiiiiiiiip",
+    "cna_fix_padding_bias": "ppiiiiiip",
+    "cna_add": "pppLip",
+    "cna_lowrank2_pack": "ppppiiiiiip",
+    "cna_lowrank2_fused_forward": "pppppiiiiiiiip",
+    "cna_lowrank2_fused_supported": "iiiiii",
+    "cna_maxpool2x2": "ppiiiiip",
+    "cna_svd_small_batched": "ppppiiip",
+    "cna_lowrank1_svd_fit": "piiippp",
+    "cna_msca_equiv_kernel": "pppppiipppp",
+}
+
+
+def lib():
+    """The loaded shared library (loads on first use; raises if it was not built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python convnet-approximater_b200/build.py` "
+                "(this backend has no CPU or eager-PyTorch fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, sig in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype = c_int
+            fn.argtypes = [{"p": c_void_p, "i": c_int, "L": ctypes.c_longlong}[ch] for ch in sig]
+        L.cna_last_error.restype = ctypes.c_char_p
+        L.cna_launch_count.restype = ctypes.c_ulonglong
+        L.cna_version.restype = c_int
+        _lib = L
+    return _lib
+
+
+def exported_symbols():
+    return list(_SIGS) + ["cna_last_error", "cna_launch_count", "cna_version"]
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError("cna_b200: " + lib().cna_last_error().decode())
+
+
+def launch_count() -> int:
+    return int(lib().cna_launch_count())
+
+
+def dtype_code(dt) -> int:
+    if dt == torch.float32:
+        return F32
+    if dt == torch.bfloat16:
+        return BF16
+    raise TypeError(f"cna_b200 supports float32 and bfloat16 tensors, got {dt}")
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("cna_b200: tensor is not on a CUDA device — this backend has no CPU fallback")
+
+
+_checked_devices = set()
+
+
+def _ready(t):
+    require_cuda(t)
+    dev = t.device.index
+    if dev not in _checked_devices:
+        with torch.cuda.device(dev):
+            _check(lib().cna_device_check())
+        _checked_devices.add(dev)
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+# ------------------------------------------------------------------------------------------- #
+# layout
+# ------------------------------------------------------------------------------------------- #
+def to_nhwc(x: torch.Tensor, c_pad: int | None = None, dtype=None) -> torch.Tensor:
+    """Logical-NCHW tensor -> contiguous (B,H,W,c_pad) tensor.  Zero-copy for channels_last input."""
+    _ready(x)
+    B, C, H, W = x.shape
+    c_pad = C if c_pad is None else c_pad
+    dtype = x.dtype if dtype is None else dtype
+    v = x.permute(0, 2, 3, 1)
+    if c_pad == C and dtype == x.dtype and v.is_contiguous():
+        return v
+    if not x.is_contiguous():
+        x = x.contiguous()  # exotic strides: torch re-strides, the library transposes
+    out = torch.empty((B, H, W, c_pad), device=x.device, dtype=dtype)
+    with torch.cuda.device(x.device):
+        _check(lib().cna_nchw_to_nhwc(_p(x), _p(out), B, C, H, W, c_pad, dtype_code(x.dtype), dtype_code(dtype),
+                                      _stream(x)))
+    return out
+
+
+def from_nhwc(y: torch.Tensor, C: int | None = None) -> torch.Tensor:
+    """(B,H,W,c_pad) buffer -> logical NCHW view (channels_last strides); copies only to drop padding."""
+    B, H, W, cp = y.shape
+    if C is None or C == cp:
+        return y.permute(0, 3, 1, 2)
+    return y[..., :C].permute(0, 3, 1, 2)
+
+
+def to_nchw_contiguous(y: torch.Tensor, C: int | None = None, dtype=None) -> torch.Tensor:
+    """(B,H,W,c_pad) buffer -> NCHW-contiguous tensor through the library's transpose kernel."""
+    _ready(y)
+    B, H, W, cp = y.shape
+    C = cp if C is None else C
+    dtype = y.dtype if dtype is None else dtype
+    out = torch.empty((B, C, H, W), device=y.device, dtype=dtype)
+    with torch.cuda.device(y.device):
+        _check(lib().cna_nhwc_to_nchw(_p(y), _p(out), B, C, H, W, cp, dtype_code(y.dtype), dtype_code(dtype),
+                                      _stream(y)))
+    return out
+
+
+# ------------------------------------------------------------------------------------------- #
+# weight packing
+# ------------------------------------------------------------------------------------------- #
+def _f32c(w):
+    return w.detach().to(torch.float32).contiguous()
+
+
+def pack_taps(w: torch.Tensor, dtype, o_pad=None, i_pad=None) -> torch.Tensor:
+    """Dense conv weight (O,I,kh,kw) with kh==1 or kw==1 -> packed [taps][i_pad][o_pad]."""
+    _ready(w)
+    O, I, kh, kw = w.shape
+    assert kh == 1 or kw == 1, "tap convs have a (d,1) or (1,d) filter"
+    taps = kh * kw
+    o_pad = O if o_pad is None else o_pad
+    i_pad = I if i_pad is None else i_pad
+    out = torch.empty((taps, i_pad, o_pad), device=w.device, dtype=dtype)
+    wf = _f32c(w)
+    with torch.cuda.device(w.device):
+        _check(lib().cna_pack_taps_weight(_p(wf), _p(out), O, I, taps, o_pad, i_pad, dtype_code(dtype), _stream(w)))
+    return out
+
+
+def pack_dw(w: torch.Tensor, dtype) -> torch.Tensor:
+    """Depthwise weight (Cout,1,kh,kw) -> packed [kh*kw][Cout]."""
+    _ready(w)
+    Co, one, kh, kw = w.shape
+    assert one == 1
+    out = torch.empty((kh * kw, Co), device=w.device, dtype=dtype)
+    wf = _f32c(w)
+    with torch.cuda.device(w.device):
+        _check(lib().cna_pack_dw_weight(_p(wf), _p(out), Co, kh, kw, dtype_code(dtype), _stream(w)))
+    return out
+
+
+# ------------------------------------------------------------------------------------------- #
+# compute
+# ------------------------------------------------------------------------------------------- #
+def conv_taps(x, wpk, bias, N, taps, axis, stride=(1, 1), pad=0, relu=False, gate=None):
+    """x (B,H,W,C) NHWC; wpk [taps][C][N]; bias fp32 (N,) or None -> (B,Ho,Wo,N)."""
+    _ready(x)
+    B, H, W, C = x.shape
+    assert wpk.shape == (taps, C, N) and wpk.dtype == x.dtype, (wpk.shape, (taps, C, N), wpk.dtype, x.dtype)
+    sh, sw = stride
+    Ho = (H + 2 * pad - taps) // sh + 1 if axis == 0 else (H - 1) // sh + 1
+    Wo = (W + 2 * pad - taps) // sw + 1 if axis == 1 else (W - 1) // sw + 1
+    y = torch.empty((B, Ho, Wo, N), device=x.device, dtype=x.dtype)
+    if gate is not None:
+        assert gate.shape == y.shape and gate.dtype == x.dtype and gate.is_contiguous()
+    with torch.cuda.device(x.device):
+        _check(lib().cna_conv_taps_forward(_p(x), _p(wpk), _p(bias), _p(gate), _p(y), B, H, W, C, N, taps, axis,
+                                           sh, sw, pad, int(relu), dtype_code(x.dtype), _stream(x)))
+    return y
+
+
+def dwconv(x, wpk, bias, mult, kh, kw, stride=(1, 1), pad=(0, 0), res=None, add=None):
+    """Depthwise conv, x (B,H,W,Cin) NHWC, wpk [kh*kw][Cin*mult]."""
+    _ready(x)
+    B, H, W, C = x.shape
+    sh, sw = stride
+    ph, pw = pad
+    assert wpk.shape == (kh * kw, C * mult) and wpk.dtype == x.dtype
+    Ho = (H + 2 * ph - kh) // sh + 1
+    Wo = (W + 2 * pw - kw) // sw + 1
+    y = torch.empty((B, Ho, Wo, C * mult), device=x.device, dtype=x.dtype)
+    res_p = 0
+    if res is not None:
+        assert res.dtype == torch.float32 and res.is_contiguous() and res.shape[:2] == (2, C * mult)
+        res_p = res.shape[2]
+    if add is not None:
+        assert add.shape == y.shape and add.dtype == x.dtype and add.is_contiguous()
+    with torch.cuda.device(x.device):
+        _check(lib().cna_dwconv_forward(_p(x), _p(wpk), _p(bias), _p(res), res_p, _p(add), _p(y), B, H, W, C, mult,
+                                        kh, kw, sh, sw, ph, pw, dtype_code(x.dtype), _stream(x)))
+    return y
+
+
+def fix_padding_bias_(x_nhwc, res):
+    """In place on an NHWC tensor."""
+    _ready(x_nhwc)
+    B, H, W, C = x_nhwc.shape
+    assert res.dtype == torch.float32 and res.is_contiguous() and res.shape[:2] == (2, C)
+    with torch.cuda.device(x_nhwc.device):
+        _check(lib().cna_fix_padding_bias(_p(x_nhwc), _p(res), B, H, W, C, res.shape[2], dtype_code(x_nhwc.dtype),
+                                          _stream(x_nhwc)))
+    return x_nhwc
+
+
+def add(a, b):
+    _ready(a)
+    assert a.shape == b.shape and a.dtype == b.dtype and a.is_contiguous() and b.is_contiguous()
+    out = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        _check(lib().cna_add(_p(a), _p(b), _p(out), a.numel(), dtype_code(a.dtype), _stream(a)))
+    return out
+
+
+def maxpool2x2(x):
+    _ready(x)
+    B, H, W, C = x.shape
+    y = torch.empty((B, H // 2, W // 2, C), device=x.device, dtype=x.dtype)
+    with torch.cuda.device(x.device):
+        _check(lib().cna_maxpool2x2(_p(x), _p(y), B, H, W, C, dtype_code(x.dtype), _stream(x)))
+    return y
+
+
+def round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+def lowrank2_k_pad(K):
+    for kp in (16, 32, 64):
+        if K <= kp:
+            return kp
+    return None
+
+
+def lowrank2_fused_supported(H, W, C, K, N, d):
+    kp = lowrank2_k_pad(K)
+    if kp is None:
+        return False
+    return bool(lib().cna_lowrank2_fused_supported(H, W, round_up(C, 16), kp, N, d))
+
+
+def lowrank2_pack(v_w, h_w):
+    """v_w (K,C,d,1), h_w (N,K,1,d) -> bf16 (wv [d][k_pad][c_pad], wh [d][N][k_pad])."""
+    _ready(v_w)
+    K, C, d, _ = v_w.shape
+    N = h_w.shape[0]
+    c_pad, k_pad = round_up(C, 16), lowrank2_k_pad(K)
+    wv = torch.empty((d, k_pad, c_pad), device=v_w.device, dtype=torch.bfloat16)
+    wh = torch.empty((d, N, k_pad), device=v_w.device, dtype=torch.bfloat16)
+    vf, hf = _f32c(v_w), _f32c(h_w)
+    with torch.cuda.device(v_w.device):
+        _check(lib().cna_lowrank2_pack(_p(vf), _p(hf), _p(wv), _p(wh), C, K, N, d, c_pad, k_pad, _stream(v_w)))
+    return wv, wh
+
+
+def lowrank2_fused(x, wv, wh, bias, relu=False):
+    """x (B,H,W,c_pad) bf16 NHWC -> (B,H,W,N) bf16; stride 1, 'same' padding."""
+    _ready(x)
+    B, H, W, cp = x.shape
+    d, kp, cp2 = wv.shape
+    N = wh.shape[1]
+    assert cp == cp2 and x.dtype == torch.bfloat16 and x.is_contiguous()
+    y = torch.empty((B, H, W, N), device=x.device, dtype=torch.bfloat16)
+    with torch.cuda.device(x.device):
+        _check(lib().cna_lowrank2_fused_forward(_p(x), _p(wv), _p(wh), _p(bias), _p(y), B, H, W, cp, kp, N, d,
+                                                int(relu), _stream(x)))
+    return y
+
+
+# ------------------------------------------------------------------------------------------- #
+# fitting step
+# ------------------------------------------------------------------------------------------- #
+def svd_small(A: torch.Tensor):
+    """Batched SVD of small fp32 matrices A (..., m, n), min(m,n) <= max(m,n) <= 64 -> (U, S, Vh), thin."""
+    _ready(A)
+    *lead, m, n = A.shape
+    Af = A.detach().to(torch.float32).reshape(-1, m, n)
+    if m < n:   # A = U S Vh  <=>  A^T = Vh^T S U^T
+        U2, S, Vh2 = svd_small(Af.transpose(1, 2).contiguous())
+        return (Vh2.transpose(1, 2).reshape(*lead, m, m), S.reshape(*lead, m), U2.transpose(1, 2).reshape(*lead, m, n))
+    Af = Af.contiguous()
+    nb = Af.shape[0]
+    U = torch.empty((nb, m, n), device=A.device, dtype=torch.float32)
+    S = torch.empty((nb, n), device=A.device, dtype=torch.float32)
+    Vh = torch.empty((nb, n, n), device=A.device, dtype=torch.float32)
+    with torch.cuda.device(A.device):
+        _check(lib().cna_svd_small_batched(_p(Af), _p(U), _p(S), _p(Vh), nb, m, n, _stream(A)))
+    return U.reshape(*lead, m, n), S.reshape(*lead, n), Vh.reshape(*lead, n, n)
+
+
+def lowrank1_svd_fit(W2d: torch.Tensor, M: int):
+    """W2d (R, q) fp32 -> weights (R, M), bases (M, q)."""
+    _ready(W2d)
+    R, q = W2d.shape
+    Wf = _f32c(W2d)
+    weights = torch.empty((R, M), device=W2d.device, dtype=torch.float32)
+    bases = torch.empty((M, q), device=W2d.device, dtype=torch.float32)
+    with torch.cuda.device(W2d.device):
+        _check(lib().cna_lowrank1_svd_fit(_p(Wf), R, q, M, _p(weights), _p(bases), _stream(W2d)))
+    return weights, bases
+
+
+def msca_equiv_kernel(w1s, b1s, w2s, b2s):
+    """Lists over branches of conv1.weight (C,1,1,k), conv1.bias (C,)|None, conv2.weight (C,1,k,1), conv2.bias."""
+    _ready(w1s[0])
+    dev = w1s[0].device
+    C = w1s[0].shape[0]
+    ks = [int(w.shape[-1]) for w in w1s]
+    K = max(ks)
+    w1cat = torch.cat([_f32c(w).reshape(-1) for w in w1s])
+    w2cat = torch.cat([_f32c(w).reshape(-1) for w in w2s])
+    zero = torch.zeros(C, device=dev, dtype=torch.float32)
+    b1 = torch.stack([zero if b is None else _f32c(b) for b in b1s]).contiguous()
+    b2 = torch.stack([zero if b is None else _f32c(b) for b in b2s]).contiguous()
+    weight = torch.empty((C, 1, K, K), device=dev, dtype=torch.float32)
+    bias = torch.empty((C,), device=dev, dtype=torch.float32)
+    res = torch.empty((2, C, K // 2), device=dev, dtype=torch.float32)
+    ks_arr = (c_int * len(ks))(*ks)
+    with torch.cuda.device(dev):
+        _check(lib().cna_msca_equiv_kernel(_p(w1cat), _p(b1), _p(w2cat), _p(b2), ctypes.cast(ks_arr, c_void_p),
+                                           len(ks), C, _p(weight), _p(bias), _p(res), _stream(weight)))
+    return weight, bias, res

@@ -1,0 +1,73 @@
+"""NHWC-level functional ops over stock `nn.Conv2d` parameter containers.
+
+The reference keeps every weight in a plain `nn.Conv2d` (`.weight.data = ...` assignments in
+core/low_rank_exp.py:181-184 and core/msca_rep.py:149-168 rely on it), so this backend keeps the
+same containers — identical state_dict keys, default initialisation and `.to()` behaviour — and
+never calls their `forward`.  Kernels want packed / cast copies of the weights; those are cached
+on the owning module and refreshed when a parameter's storage or version counter changes.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from approx import backend as B
+
+
+def _sig(params, dtype):
+    return tuple((p.data_ptr(), p._version, str(p.device), p.dtype, tuple(p.shape)) if p is not None else None
+                 for p in params) + (dtype,)
+
+
+def cached(owner: nn.Module, key, params, dtype, build):
+    """Memoise `build()` on `owner`, keyed on the identity+version of `params`."""
+    store = owner.__dict__.setdefault("_cna_cache", {})
+    sig = _sig(params, dtype)
+    hit = store.get(key)
+    if hit is not None and hit[0] == sig:
+        return hit[1]
+    val = build()
+    store[key] = (sig, val)
+    return val
+
+
+def bias_f32(conv):
+    b = getattr(conv, "bias", None)
+    if b is None:
+        return None
+    return cached(conv, "bias_f32", (b,), torch.float32, lambda: b.detach().to(torch.float32).contiguous())
+
+
+def is_depthwise(conv: nn.Conv2d) -> bool:
+    return conv.groups == conv.in_channels and conv.groups > 1 or (conv.groups == 1 and conv.in_channels == 1)
+
+
+def dw(conv: nn.Conv2d, x, res=None, add=None):
+    """Depthwise (groups=in_channels, any multiplier) conv described by `conv` applied to NHWC `x`."""
+    assert conv.groups == conv.in_channels and conv.dilation == (1, 1), "not a depthwise conv"
+    mult = conv.out_channels // conv.in_channels
+    kh, kw = conv.kernel_size
+    wpk = cached(conv, "dw_w", (conv.weight,), x.dtype, lambda: B.pack_dw(conv.weight, x.dtype))
+    return B.dwconv(x, wpk, bias_f32(conv), mult, kh, kw, tuple(conv.stride), tuple(conv.padding), res=res, add=add)
+
+
+def dense_taps(conv: nn.Conv2d, x, relu=False, gate=None):
+    """Dense conv whose filter is (d,1), (1,d) or (1,1), applied to NHWC `x`."""
+    assert conv.groups == 1 and conv.dilation == (1, 1)
+    kh, kw = conv.kernel_size
+    assert kh == 1 or kw == 1, "dense convs on this path are 1-D tap runs"
+    axis = 0 if kw == 1 and kh > 1 else 1
+    taps = kh * kw
+    pad = conv.padding[0] if axis == 0 else conv.padding[1]
+    other = conv.padding[1] if axis == 0 else conv.padding[0]
+    assert other == 0, "padding across the tap axis is not used on this path"
+    wpk = cached(conv, "taps_w", (conv.weight,), x.dtype, lambda: B.pack_taps(conv.weight, x.dtype))
+    return B.conv_taps(x, wpk, bias_f32(conv), conv.out_channels, taps, axis, tuple(conv.stride), pad,
+                       relu=relu, gate=gate)
+
+
+def check_input(x: torch.Tensor):
+    if x.dim() != 4:
+        raise ValueError(f"expected a (B,C,H,W) tensor, got shape {tuple(x.shape)}")
+    B.require_cuda(x)
+    B.dtype_code(x.dtype)

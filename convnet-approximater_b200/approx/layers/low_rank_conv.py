@@ -1,0 +1,149 @@
+"""Low-rank expanded convolutions (Jaderberg et al., arXiv:1405.3866) on the B200 backend.
+
+Drop-in for the reference's src/approx/layers/low_rank_conv.py: same class names, constructor
+arguments, attribute names and state_dict keys; `forward` runs this library's CUDA kernels on
+NHWC data instead of chaining `nn.Conv2d` calls (reference lines 24-25, 51-52, 83-84).
+"""
+from typing import Optional, Union
+
+import torch
+from torch import nn
+
+from approx import backend as B
+from approx.utils.general import to_2tuple
+from . import _ops
+from .substituton import LAYER
+
+
+class SeparableConv(nn.Module):
+    """Depthwise-with-multiplier (d,1) conv followed by a depthwise (1,d) conv, both bias-free
+    (reference low_rank_conv.py:9-25): the separable form of a grouped C -> C*M conv."""
+
+    def __init__(self, in_channels: int, num_bases: int, kernel_size: tuple, stride: tuple, padding: tuple):
+        super().__init__()
+        wide = in_channels * num_bases
+        self.v_conv = nn.Conv2d(in_channels, wide, (kernel_size[0], 1), (stride[0], 1), (padding[0], 0),
+                                groups=in_channels, bias=False)
+        self.h_conv = nn.Conv2d(wide, wide, (1, kernel_size[1]), (1, stride[1]), (0, padding[1]),
+                                groups=wide, bias=False)
+
+    def forward_nhwc(self, x):
+        return _ops.dw(self.h_conv, _ops.dw(self.v_conv, x))
+
+    def forward(self, x):
+        _ops.check_input(x)
+        return B.from_nhwc(self.forward_nhwc(B.to_nhwc(x)))
+
+
+@LAYER.register_module()
+class LowRankExpConvV1(nn.Module):
+    """Scheme 1: M shared d x d basis filters per input channel (`s_conv`, grouped, WITH bias as in the
+    reference, low_rank_conv.py:44-48) mixed by a 1x1 conv (`d_conv`).  Output channel c*M+m of `s_conv`
+    is input channel c filtered by basis m."""
+
+    def __init__(self, in_channels: int, out_channels: int,
+                 kernel_size: Union[int, tuple], stride: Union[int, tuple], padding: Union[int, tuple],
+                 num_base: int, decomp: bool = False):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.kernel_size = to_2tuple(kernel_size)
+        self.stride = to_2tuple(stride)
+        self.padding = to_2tuple(padding)
+        self.num_base = num_base
+        wide = in_channels * num_base
+        if decomp:
+            self.s_conv = SeparableConv(in_channels, num_base, self.kernel_size, self.stride, self.padding)
+        else:
+            self.s_conv = nn.Conv2d(in_channels, wide, self.kernel_size, self.stride, self.padding,
+                                    groups=in_channels)
+        self.d_conv = nn.Conv2d(wide, out_channels, 1)
+
+    @property
+    def bias(self):
+        return self.d_conv.bias
+
+    def forward_nhwc(self, x):
+        t = self.s_conv.forward_nhwc(x) if isinstance(self.s_conv, SeparableConv) else _ops.dw(self.s_conv, x)
+        return _ops.dense_taps(self.d_conv, t)
+
+    def forward(self, x):
+        _ops.check_input(x)
+        return B.from_nhwc(self.forward_nhwc(B.to_nhwc(x)))
+
+    def decomp(self):
+        """Replace every d x d basis by its best rank-1 split v (d,1) * h (1,d) (reference :58-66).
+        Idempotent.  The batched small SVD runs on the device (approx.core.fit)."""
+        if not isinstance(self.s_conv, nn.Conv2d):
+            return
+        from approx.core import fit
+        sep = SeparableConv(self.in_channels, self.num_base, self.kernel_size, self.stride, self.padding)
+        v, h = fit.rank1_split(self.s_conv.weight.data)
+        sep.v_conv.weight.data = v
+        sep.h_conv.weight.data = h
+        self.s_conv = sep
+
+
+@LAYER.register_module()
+class LowRankExpConvV2(nn.Module):
+    """Scheme 2: a dense vertical (d,1) conv into `num_base` = K channels (no bias) followed by a
+    horizontal (1,d) conv with bias.
+
+    `out_channels=None` reproduces the class exactly as the reference ships it (low_rank_conv.py:75-81:
+    `h_conv` depthwise K -> K, output has K channels).  `out_channels=N` builds the true scheme 2 of the
+    paper — dense `h_conv` K -> N, weight (N,K,1,d) — which is the layer BASELINE's configs name.  With
+    bf16 inputs, stride 1 and 'same' padding the two convs run as ONE fused tcgen05 kernel that keeps the
+    K-channel intermediate in shared memory."""
+
+    def __init__(self, in_channels: int, num_base: int, kernel_size: tuple, stride: tuple, padding: tuple,
+                 out_channels: Optional[int] = None):
+        super().__init__()
+        kernel_size, stride, padding = to_2tuple(kernel_size), to_2tuple(stride), to_2tuple(padding)
+        self.in_channels = in_channels
+        self.num_base = num_base
+        self.out_channels = num_base if out_channels is None else out_channels
+        self.kernel_size, self.stride, self.padding = kernel_size, stride, padding
+        self.v_conv = nn.Conv2d(in_channels, num_base, (kernel_size[0], 1), (stride[0], 1), (padding[0], 0), bias=False)
+        if out_channels is None:
+            self.h_conv = nn.Conv2d(num_base, num_base, (1, kernel_size[1]), (1, stride[1]), (0, padding[1]),
+                                    groups=num_base)
+        else:
+            self.h_conv = nn.Conv2d(num_base, out_channels, (1, kernel_size[1]), (1, stride[1]), (0, padding[1]))
+        self.fuse_relu = False  # set by callers that own the following ReLU (VGG trunk)
+
+    @property
+    def bias(self):
+        return self.h_conv.bias
+
+    @property
+    def dense(self) -> bool:
+        return self.h_conv.groups == 1
+
+    def _fusable(self, x_dtype, H, W) -> bool:
+        kh, kw = self.kernel_size
+        return (self.dense and x_dtype == torch.bfloat16 and kh == kw and kh % 2 == 1
+                and self.stride == (1, 1) and self.padding == (kh // 2, kw // 2)
+                and B.lowrank2_fused_supported(H, W, self.in_channels, self.num_base, self.out_channels, kh))
+
+    def forward_nhwc(self, x, c_in=None):
+        """x: (B,H,W,C or c_pad) NHWC."""
+        _, H, W, cx = x.shape
+        if self._fusable(x.dtype, H, W):
+            c_pad = B.round_up(self.in_channels, 16)
+            if cx != c_pad:
+                raise ValueError(f"fused path wants {c_pad} input channels (zero padded), got {cx}")
+            wv, wh = _ops.cached(self, "lr2_pack", (self.v_conv.weight, self.h_conv.weight), torch.bfloat16,
+                                 lambda: B.lowrank2_pack(self.v_conv.weight, self.h_conv.weight))
+            return B.lowrank2_fused(x, wv, wh, _ops.bias_f32(self.h_conv), relu=self.fuse_relu)
+        t = _ops.dense_taps(self.v_conv, x)
+        if self.dense:
+            return _ops.dense_taps(self.h_conv, t, relu=self.fuse_relu)
+        if self.fuse_relu:
+            raise RuntimeError("fuse_relu is only available with a dense h_conv (out_channels given)")
+        return _ops.dw(self.h_conv, t)
+
+    def forward(self, x):
+        _ops.check_input(x)
+        H, W = x.shape[2:]
+        c_pad = B.round_up(self.in_channels, 16) if self._fusable(x.dtype, H, W) else None
+        return B.from_nhwc(self.forward_nhwc(B.to_nhwc(x, c_pad)))

@@ -1,0 +1,49 @@
+"""VGG-16 convolutional trunk with every 3x3 conv replaced by a scheme-2 low-rank expansion.
+
+The reference ships AlexNet and MSCAN only; BASELINE.json's headline configuration ("VGG-16, all 3x3
+conv layers replaced by scheme-2 low-rank expansions, bf16 inference, batch 256 at 224x224") is built
+here from the same layer class the registry exposes (`LowRankExpConvV2` with a dense h_conv).
+The trunk runs NHWC end to end: 13 fused low-rank convs (ReLU in their epilogue) and 5 2x2 max-pools.
+"""
+from typing import Sequence, Union
+
+import torch
+from torch import nn
+
+from approx import backend as B
+from approx.layers import LowRankExpConvV2
+
+# (in_channels, out_channels) per conv, 'M' = 2x2 max-pool
+VGG16_CFG = [(3, 64), (64, 64), "M", (64, 128), (128, 128), "M", (128, 256), (256, 256), (256, 256), "M",
+             (256, 512), (512, 512), (512, 512), "M", (512, 512), (512, 512), (512, 512), "M"]
+
+
+class VGG16Scheme2Trunk(nn.Module):
+    def __init__(self, rank: Union[int, Sequence[int]] = 64):
+        super().__init__()
+        convs = [c for c in VGG16_CFG if c != "M"]
+        ranks = [rank] * len(convs) if isinstance(rank, int) else list(rank)
+        assert len(ranks) == len(convs)
+        self.features = nn.ModuleList()
+        it = iter(ranks)
+        for c in VGG16_CFG:
+            if c == "M":
+                self.features.append(nn.Identity())  # placeholder: pooling is done by the backend kernel
+            else:
+                layer = LowRankExpConvV2(c[0], next(it), (3, 3), (1, 1), (1, 1), out_channels=c[1])
+                layer.fuse_relu = True
+                self.features.append(layer)
+
+    def conv_layers(self):
+        return [m for m in self.features if isinstance(m, LowRankExpConvV2)]
+
+    def forward_nhwc(self, x):
+        """x: (B,H,W,16) bf16 (3 image channels zero-padded to 16) or (B,H,W,3) fp32."""
+        for m in self.features:
+            x = B.maxpool2x2(x) if isinstance(m, nn.Identity) else m.forward_nhwc(x)
+        return x
+
+    def forward(self, x):
+        """x: (B,3,H,W) logical NCHW, bf16 (fused tcgen05 path) or fp32 (exact FFMA path)."""
+        c_pad = 16 if x.dtype == torch.bfloat16 else None
+        return B.from_nhwc(self.forward_nhwc(B.to_nhwc(x, c_pad)))

@@ -1,0 +1,33 @@
+// Library-level C ABI: error string, device check, launch counter.
+#include "common.cuh"
+
+#include <atomic>
+
+namespace cna {
+static thread_local std::string g_err;
+static std::atomic<unsigned long long> g_launches{0};
+void set_error(const std::string& msg) { g_err = msg; }
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+}  // namespace cna
+
+extern "C" {
+
+int cna_version(void) { return 100; }
+
+const char* cna_last_error(void) { return cna::g_err.c_str(); }
+
+unsigned long long cna_launch_count(void) { return cna::g_launches.load(); }
+
+int cna_device_check(void) {
+    int dev = 0;
+    CNA_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CNA_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) {
+        CNA_FAIL(std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                 std::to_string(prop.minor) + "; this library is built for sm_100a (B200) only");
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,57 @@
+// Shared helpers for the sm_100a kernels of the ConvNet-Approximater hot path.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/cna_b200.h"
+
+namespace cna {
+
+// ---- error plumbing (thread-local message, integer status over the C ABI) -------------------
+void set_error(const std::string& msg);
+void count_launch(int n = 1);
+
+#define CNA_FAIL(msg)                                                                   \
+    do {                                                                                \
+        ::cna::set_error(std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": " + (msg)); \
+        return 1;                                                                       \
+    } while (0)
+
+#define CNA_CHECK(cond, msg) \
+    do { if (!(cond)) CNA_FAIL(std::string("check failed: " #cond " — ") + (msg)); } while (0)
+
+#define CNA_CUDA(expr)                                                                  \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess) CNA_FAIL(std::string(#expr " -> ") + cudaGetErrorString(_e)); \
+    } while (0)
+
+// After a launch: catch configuration errors without synchronising.
+#define CNA_LAUNCH_OK()                                                                 \
+    do {                                                                                \
+        cudaError_t _e = cudaGetLastError();                                            \
+        if (_e != cudaSuccess) CNA_FAIL(std::string("kernel launch: ") + cudaGetErrorString(_e)); \
+        ::cna::count_launch();                                                          \
+    } while (0)
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+// ---- element type helpers ---------------------------------------------------------------------
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename T> __device__ __forceinline__ T ldg(const T* p) { return __ldg(p); }
+template <> __device__ __forceinline__ __nv_bfloat16 ldg<__nv_bfloat16>(const __nv_bfloat16* p) {
+    unsigned short u = __ldg(reinterpret_cast<const unsigned short*>(p));
+    return __ushort_as_bfloat16(u);
+}
+
+}  // namespace cna

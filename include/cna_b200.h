@@ -1,0 +1,125 @@
+/*
+ * cna_b200.h — C ABI of the B200 (sm_100a) backend for ConvNet-Approximater's hot path.
+ *
+ * The reference (ashun989/ConvNet-Approximater) is pure Python/PyTorch and has no FFI of its
+ * own; the "interface each entry point replaces" is therefore the `forward()` / `optimize()`
+ * body of the reference module or app named beside it (paths relative to the reference root).
+ * INTEGRATION.md shows the ctypes binding a maintainer adds to those bodies.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - activations are NHWC (channels-last) contiguous: x[b][h][w][c];
+ *   - `dtype` selects the activation AND packed-weight element type: CNA_F32 or CNA_BF16
+ *     (bf16 kernels accumulate in fp32 and round intermediates to bf16 exactly where the
+ *     reference's bf16 modules materialise a tensor); biases / residues are always fp32;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are asynchronous;
+ *   - return value 0 = success, non-zero = error; cna_last_error() gives the message of the last
+ *     failure on the calling thread.  There is NO CPU fallback: a missing/non-sm_100 device is an error.
+ */
+#ifndef CNA_B200_H
+#define CNA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum { CNA_F32 = 0, CNA_BF16 = 1 } cna_dtype;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int         cna_version(void);
+const char* cna_last_error(void);
+/* 0 iff the current CUDA device is compute capability 10.x (B200). */
+int         cna_device_check(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches). */
+unsigned long long cna_launch_count(void);
+
+/* ---- layout (boundary helpers: the reference's tensors are logical NCHW) ------------------ */
+/* src NCHW (src_dtype) -> dst NHWC with channel count c_pad >= C (extra channels zero-filled). */
+int cna_nchw_to_nhwc(const void* src, void* dst, int B, int C, int H, int W, int c_pad,
+                     int src_dtype, int dst_dtype, void* stream);
+/* src NHWC with c_pad channels -> dst NCHW with C channels. */
+int cna_nhwc_to_nchw(const void* src, void* dst, int B, int C, int H, int W, int c_pad,
+                     int src_dtype, int dst_dtype, void* stream);
+
+/* ---- weight packing ------------------------------------------------------------------------ */
+/* Dense conv weight in the reference's OIHW layout, with kh==1 or kw==1 (a run of `taps` taps),
+ * fp32:  w[o][i][t]  ->  packed[t][i_pad][o_pad] in `dtype` (zero-filled padding).
+ * Replaces nothing in the reference: it is the cache behind `.weight.data` assignments
+ * (src/approx/core/low_rank_exp.py:181-184, src/approx/core/msca_rep.py:149-168). */
+int cna_pack_taps_weight(const float* w_oit, void* packed, int O, int I, int taps,
+                         int o_pad, int i_pad, int dtype, void* stream);
+/* Depthwise weight (Cout,1,kh,kw) fp32 -> packed[kh*kw][Cout] in `dtype`. */
+int cna_pack_dw_weight(const float* w, void* packed, int Cout, int kh, int kw, int dtype, void* stream);
+
+/* ---- generic dense "tap" convolution (FFMA path; exact fp32) -------------------------------- */
+/* y[b,ho,wo,n] = act( sum_t sum_c x[b, ho*sh - pad_h + t*ah, wo*sw - pad_w + t*aw, c] * w[t][c][n] + bias[n] )
+ *               (* gate[b,ho,wo,n] if gate != NULL)
+ * axis 0: taps run along H (ah=1, aw=0, pad applies to H); axis 1: along W.  taps==1 is a 1x1 conv.
+ * Replaces: nn.Conv2d calls at src/approx/layers/low_rank_conv.py:49,79-81 (d_conv, v_conv, dense h_conv)
+ * and src/approx/layers/msca.py:23,26 (channel_mix and the `x *` gate). */
+int cna_conv_taps_forward(const void* x, const void* w_packed, const float* bias, const void* gate, void* y,
+                          int B, int H, int W, int C, int N, int taps, int axis,
+                          int stride_h, int stride_w, int pad, int relu, int dtype, void* stream);
+
+/* ---- depthwise convolution (generic) -------------------------------------------------------- */
+/* Grouped conv with groups=Cin and channel multiplier `mult`: output channel co reads input channel co/mult.
+ * w_packed[kh*kw][Cin*mult]; bias may be NULL.
+ * res/res_p: optional fused FixPaddingBias (src/approx/layers/depth_seperable_conv.py:57-61): res[2][Cout][res_p] fp32
+ * added to the top/bottom min(Ho,res_p) output rows.
+ * add: optional tensor (same shape as y) added to the result (ParallelConv's running sum,
+ * src/approx/layers/depth_seperable_conv.py:45-47).
+ * Replaces: nn.Conv2d(groups=C) at low_rank_conv.py:17-22,44-48; depth_seperable_conv.py:12-13; msca.py:18-19;
+ * core/msca_rep.py:44-45. */
+int cna_dwconv_forward(const void* x, const void* w_packed, const float* bias, const float* res, int res_p,
+                       const void* add, void* y,
+                       int B, int H, int W, int Cin, int mult, int kh, int kw,
+                       int stride_h, int stride_w, int pad_h, int pad_w, int dtype, void* stream);
+
+/* out = a + b elementwise over `count` elements (ParallelConv's identity branch). */
+int cna_add(const void* a, const void* b, void* out, long long count, int dtype, void* stream);
+
+/* In-place FixPaddingBias on an NHWC tensor (depth_seperable_conv.py:57-61). */
+int cna_fix_padding_bias(void* x, const float* res, int B, int H, int W, int C, int p, int dtype, void* stream);
+
+/* ---- scheme-2 low-rank conv, fused (tcgen05 / TMEM / TMA) ------------------------------------ */
+/* Fused  y = h_conv(v_conv(x)) + bias  for stride 1, odd d, pad d/2 ("same"), bf16 NHWC:
+ *   T[b,h,w,k] = sum_dy sum_c x[b,h+dy-d/2,w,c] * wv[dy][k][c]        (rounded to bf16, stays in shared memory)
+ *   y[b,h,w,n] = act( sum_dx sum_k T[b,h,w+dx-d/2,k] * wh[dx][n][k] + bias[n] )
+ * wv_packed: [d][k_pad][c_pad] bf16 (c contiguous), wh_packed: [d][n][k_pad] bf16 (k contiguous);
+ * build them with cna_lowrank2_pack. c_pad = C rounded up to 16, k_pad in {16,32,64}.
+ * x has c_pad channels (NHWC), y has N channels.
+ * Replaces: LowRankExpConvV2.forward, src/approx/layers/low_rank_conv.py:83-84 (true scheme 2: dense h_conv). */
+int cna_lowrank2_pack(const float* v_w /*(K,C,d,1)*/, const float* h_w /*(N,K,1,d)*/,
+                      void* wv_packed, void* wh_packed, int C, int K, int N, int d,
+                      int c_pad, int k_pad, void* stream);
+int cna_lowrank2_fused_forward(const void* x, const void* wv_packed, const void* wh_packed, const float* bias,
+                               void* y, int B, int H, int W, int c_pad, int k_pad, int N, int d,
+                               int relu, void* stream);
+/* 1 if the fused kernel supports this configuration, else 0 (caller falls back to two cna_conv_taps_forward). */
+int cna_lowrank2_fused_supported(int H, int W, int c_pad, int k_pad, int N, int d);
+
+/* ---- fitting step (device-side small linear algebra) ------------------------------------------- */
+/* Batched SVD of small matrices, A (batch,m,n) fp32 row-major with 1 <= n <= m <= 64:
+ * U (batch,m,n), S (batch,n) descending, Vh (batch,n,n).  One-sided Jacobi in fp64, one warp per matrix.
+ * Replaces torch.linalg.svd at src/approx/layers/low_rank_conv.py:61 and src/approx/core/msca_rep.py:154. */
+int cna_svd_small_batched(const float* A, float* U, float* S, float* Vh, int batch, int m, int n, void* stream);
+/* Scheme-1 SVD initialisation: W (R = N*C rows, q = d*d cols, fp32) -> weights (R,M) = U[:, :M]*sqrt(S),
+ * bases (M,q) = sqrt(S)*Vh[:M]  (zero-filled beyond rank q).  Gram matrix + Jacobi eigen-solve in fp64.
+ * Replaces numpy.linalg.svd + scaling at src/approx/core/low_rank_exp.py:110-120. */
+int cna_lowrank1_svd_fit(const float* W, int R, int q, int M, float* weights, float* bases, void* stream);
+/* MSCA equivalent kernel (src/approx/core/msca_rep.py:57-143).  nb strip branches with odd sizes ks_host[i]
+ * (ascending); w1cat / w2cat hold, branch after branch, the (C x k_i) row-major taps of conv1 (1 x k) and
+ * conv2 (k x 1); b1 / b2 are (nb, C) or NULL.  Outputs: weight (C,K,K), bias (C), res (2,C,K/2), K = max k. */
+int cna_msca_equiv_kernel(const float* w1cat, const float* b1, const float* w2cat, const float* b2,
+                          const int* ks_host, int nb, int C, float* weight, float* bias, float* res, void* stream);
+
+/* 2x2/stride-2 max pool, NHWC (VGG trunk glue between the approximated convs). */
+int cna_maxpool2x2(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNA_B200_H */

@@ -1,0 +1,122 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/cna_b200.h declares, the
+host-side mirror keeps the reference's registry names / constructor signatures / state_dict keys, and
+the product path refuses to run without CUDA (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from approx import backend
+    hdr = open(os.path.join(ROOT, "include", "cna_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(cna_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 15
+    lib = ctypes.CDLL(backend.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/cna_b200.h but not exported"
+    assert set(backend.exported_symbols()) <= set(declared)
+    assert backend.lib().cna_version() >= 100
+
+
+def test_registries_hold_the_reference_names():
+    from approx.layers import LAYER
+    from approx.core import APP
+    for n in ("LowRankExpConvV1", "LowRankExpConvV2", "MSCA", "MSCAProfile", "SimpleConv", "DummyLayer"):
+        assert n in LAYER
+    for n in ("LowRankExpV1", "MscaRep", "MscaProfile", "MscaRepProfile", "Dummy", "LowRankExpV2"):
+        assert n in APP
+    with pytest.raises(AssertionError):
+        LAYER.get("nope")
+    with pytest.raises(AssertionError):           # double registration asserts, like the reference
+        LAYER.register_module(name="MSCA", module=nn.Identity)
+
+
+def test_build_from_cfg_behaviour():
+    from approx.layers import build_layer
+    from approx.core import build_app
+    m = build_layer(dict(type="MSCA", num_channel=8, k1_size=5, k_sizes=(7, 11, 21)))
+    assert m.num_channel == 8 and m.switchable_layer() is m.sd_convs
+    app = build_app(dict(type="MscaRep", decomp=1, fix=True), deploy=False)
+    assert app.decomp == 1 and app.fix and app.src_type is type(m)
+    with pytest.raises(TypeError):
+        build_layer(dict(type="MSCA", bogus=1))
+    assert build_layer(None) is None
+
+
+def test_state_dict_keys_match_reference(golden):
+    from approx.layers import LowRankExpConvV1, LowRankExpConvV2, MSCA
+    from approx.core import MscaRep
+    g = golden("lowrank1")
+    keys = lambda prefix, gg: sorted(k[len(prefix):] for k in gg if k.startswith(prefix) and "." in k[len(prefix):]
+                                      and not k[len(prefix):].startswith("dec_"))
+    assert sorted(LowRankExpConvV1(8, 12, 3, 1, 1, num_base=4).state_dict()) == keys("a_", g)
+    assert sorted(LowRankExpConvV1(8, 12, 3, 1, 1, num_base=4, decomp=True).state_dict()) == \
+        sorted(k[len("a_dec_"):] for k in g if k.startswith("a_dec_"))
+    g2 = golden("lowrank2_shipped")
+    m2 = LowRankExpConvV2(16, 8, (3, 3), (1, 1), (1, 1))
+    assert sorted(m2.state_dict()) == keys("a_", g2)
+    assert tuple(m2.h_conv.weight.shape) == tuple(g2["a_h_conv.weight"].shape)        # depthwise, as shipped
+    assert tuple(LowRankExpConvV2(16, 8, (3, 3), (1, 1), (1, 1), out_channels=32).h_conv.weight.shape) == (32, 8, 1, 3)
+    gm = golden("msca")
+    src = MSCA(8, 5, (7, 11, 21))
+    assert sorted(src.state_dict()) == keys("src_", gm)
+    for decomp, fix in [(0, True), (0, False), (1, True), (2, True), (4, True), (3, False)]:
+        tag = f"d{decomp}{'f' if fix else 'n'}_"
+        sub = MscaRep(decomp=decomp, fix=fix).initialize(src)      # structure only: no device needed
+        assert sorted(sub.new.state_dict()) == keys(tag, gm), tag
+        assert sorted(sub.state_dict()) == sorted([f"old.{k}" for k in src.state_dict()] +
+                                                  [f"new.{k}" for k in sub.new.state_dict()])
+    assert isinstance(MscaRep(decomp=1, fix=True, deploy=True).initialize(src), MSCA)
+
+
+def test_same_seed_same_initialisation_as_reference(golden):
+    """Parameter containers are stock nn.Conv2d built in the reference's order, so a seed reproduces its init."""
+    from approx.layers import LowRankExpConvV2
+    torch.manual_seed(7)
+    m = LowRankExpConvV2(16, 8, (3, 3), (1, 1), (1, 1)).to(torch.bfloat16)
+    g = golden("bf16")
+    assert np.array_equal(m.v_conv.weight.detach().float().numpy(), g["v2_v_conv.weight"])
+    assert np.array_equal(m.h_conv.bias.detach().float().numpy(), g["v2_h_conv.bias"])
+
+
+def test_num_bases_cursor_and_rewind():
+    from approx.core import LowRankExpV1
+    app = LowRankExpV1(num_bases=(4, 6), max_iter=0, lmda_length=1, min_lmda=0.001, max_lmda=0.001)
+    a = app.initialize(nn.Conv2d(4, 8, 3, 1, 1)); b = app.initialize(nn.Conv2d(8, 8, 5, 1, 2))
+    assert a.new.num_base == 4 and b.new.num_base == 6 and b.new.kernel_size == (5, 5)
+    app.rewind()
+    assert app.initialize(nn.Conv2d(4, 8, 3, 1, 1)).new.num_base == 4
+    assert a.new.bias is a.new.d_conv.bias and torch.equal(a.new.bias.data, a.old.bias.data)
+    with pytest.raises(AssertionError):
+        app.initialize(nn.Linear(2, 2))
+
+
+def test_no_cpu_fallback():
+    from approx.layers import LowRankExpConvV2, MSCA, CascadeConv, FixPaddingBias
+    x = torch.randn(1, 8, 8, 8)
+    for m in (MSCA(8, 5, (7, 11, 21)), LowRankExpConvV2(8, 4, (3, 3), (1, 1), (1, 1), out_channels=8),
+              CascadeConv(8, 7, 3, True, True), FixPaddingBias(8, 3)):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            m(x)
+    if not torch.cuda.is_available():
+        from approx.core import MscaRep
+        app = MscaRep(decomp=0, fix=True)
+        sub = app.initialize(MSCA(8, 5, (7, 11, 21)))
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            app.optimize(sub)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "convnet-approximater_b200")
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|approx_oracle", re.M)
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                assert not pat.search(open(os.path.join(dp, f)).read()), (dp, f)

@@ -1,0 +1,141 @@
+"""GPU parity tests of the generic CUDA kernels (through the C ABI via approx.backend) against the
+CPU oracle / stock torch CPU convs on the same seeded inputs.  fp32: compare4d < 1e-5 (the reference's
+threshold, tests/test_low_rank_exp.py:14); bf16: compare4d < 1e-3 against the oracle run in bf16."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import approx_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL32, TOL16 = 1e-5, 1e-3
+
+
+@pytest.fixture(scope="module")
+def B():
+    from approx import backend
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    backend.lib()
+    return backend
+
+
+def dev(t, dt=torch.float32):
+    return t.to("cuda", dt)
+
+
+def nchw(y_nhwc):
+    return y_nhwc.permute(0, 3, 1, 2).float().cpu()
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape,c_pad", [((2, 3, 5, 7), 16), ((1, 33, 9, 4), 33), ((3, 64, 8, 8), 64)])
+def test_layout_roundtrip(B, dt, shape, c_pad):
+    torch.manual_seed(0)
+    x = torch.randn(*shape).to(dt)
+    xn = B.to_nhwc(x.cuda(), c_pad)
+    assert xn.shape == (shape[0], shape[2], shape[3], c_pad)
+    ref = torch.zeros(shape[0], shape[2], shape[3], c_pad, dtype=dt)
+    ref[..., :shape[1]] = x.permute(0, 2, 3, 1)
+    assert torch.equal(xn.cpu(), ref)
+    back = B.to_nchw_contiguous(xn, shape[1])
+    assert torch.equal(back.cpu(), x)
+    # channels_last input is taken zero-copy
+    xcl = x.cuda().contiguous(memory_format=torch.channels_last)
+    assert B.to_nhwc(xcl).data_ptr() == xcl.data_ptr()
+
+
+CONV_CASES = [
+    # B, C, H, W, N, taps, axis, sh, sw, pad
+    (2, 16, 12, 10, 8, 3, 0, 1, 1, 1),
+    (2, 8, 12, 10, 24, 3, 1, 1, 1, 1),
+    (3, 6, 11, 9, 4, 5, 0, 2, 1, 2),
+    (3, 4, 11, 9, 7, 3, 1, 1, 2, 1),
+    (2, 70, 7, 9, 130, 1, 1, 1, 1, 0),
+    (1, 3, 20, 20, 64, 3, 0, 1, 1, 0),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_conv_taps_vs_torch(B, case, dt):
+    Bn, C, H, W, N, taps, axis, sh, sw, pad = case
+    torch.manual_seed(1)
+    x = torch.randn(Bn, C, H, W).to(dt)
+    w = (torch.randn(N, C, taps, 1) if axis == 0 else torch.randn(N, C, 1, taps)).to(dt)
+    b = torch.randn(N).to(dt)
+    stride = (sh, 1) if axis == 0 else (1, sw)
+    padding = (pad, 0) if axis == 0 else (0, pad)
+    ref = F.conv2d(x, w, b, stride, padding)
+    wpk = B.pack_taps(w.cuda().float(), dt)
+    y = B.conv_taps(B.to_nhwc(x.cuda()), wpk, b.float().cuda(), N, taps, axis, stride, pad)
+    assert O.compare4d(ref.float(), nchw(y)) < (TOL32 if dt == torch.float32 else TOL16)
+    # relu + gate epilogue
+    g = torch.randn_like(ref)
+    y2 = B.conv_taps(B.to_nhwc(x.cuda()), wpk, b.float().cuda(), N, taps, axis, stride, pad, relu=True,
+                     gate=B.to_nhwc(g.cuda()).contiguous())
+    ref2 = (torch.relu(ref) * g)
+    assert O.compare4d(ref2.float(), nchw(y2)) < (TOL32 if dt == torch.float32 else 3e-3)
+
+
+DW_CASES = [
+    # B, C, H, W, mult, kh, kw, sh, sw, ph, pw
+    (2, 8, 9, 11, 4, 3, 3, 1, 1, 1, 1),
+    (2, 6, 13, 12, 3, 5, 5, 2, 2, 2, 2),
+    (2, 8, 24, 26, 1, 1, 21, 1, 1, 0, 10),
+    (2, 8, 7, 9, 1, 21, 1, 1, 1, 10, 0),
+    (1, 5, 7, 9, 1, 21, 21, 1, 1, 10, 10),
+    (2, 6, 10, 8, 2, 3, 1, 2, 1, 1, 0),
+]
+
+
+@pytest.mark.parametrize("case", DW_CASES)
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_dwconv_vs_torch(B, case, dt):
+    Bn, C, H, W, mult, kh, kw, sh, sw, ph, pw = case
+    torch.manual_seed(2)
+    x = torch.randn(Bn, C, H, W).to(dt)
+    w = (torch.randn(C * mult, 1, kh, kw) / (kh * kw) ** 0.5).to(dt)
+    b = torch.randn(C * mult).to(dt)
+    ref = F.conv2d(x, w, b, (sh, sw), (ph, pw), groups=C)
+    wpk = B.pack_dw(w.cuda().float(), dt)
+    y = B.dwconv(B.to_nhwc(x.cuda()), wpk, b.float().cuda(), mult, kh, kw, (sh, sw), (ph, pw))
+    tol = TOL32 if dt == torch.float32 else TOL16
+    assert O.compare4d(ref.float(), nchw(y)) < tol
+    # fused running-sum + FixPaddingBias residues
+    add = torch.randn_like(ref)
+    res = torch.randn(2, C * mult, 10)
+    ref2 = O.fix_padding_bias(ref.clone(), res.to(dt), 10) + add
+    y2 = B.dwconv(B.to_nhwc(x.cuda()), wpk, b.float().cuda(), mult, kh, kw, (sh, sw), (ph, pw),
+                  res=res.to(dt).float().cuda(), add=B.to_nhwc(add.cuda()).contiguous())
+    assert O.compare4d(ref2.float(), nchw(y2)) < (tol if dt == torch.float32 else 3e-3)
+
+
+@pytest.mark.parametrize("H", [24, 7, 20])
+def test_fix_padding_bias_inplace(B, H):
+    torch.manual_seed(3)
+    x = torch.randn(2, 6, H, 5)
+    res = torch.randn(2, 6, 10)
+    ref = O.fix_padding_bias(x.clone(), res, 10)
+    xn = B.to_nhwc(x.cuda()).contiguous()
+    B.fix_padding_bias_(xn, res.cuda())
+    assert torch.allclose(nchw(xn), ref, atol=1e-6)
+
+
+def test_maxpool_and_add(B):
+    torch.manual_seed(4)
+    for dt, C in [(torch.float32, 5), (torch.bfloat16, 16), (torch.bfloat16, 6)]:
+        x = torch.randn(2, C, 8, 6).to(dt)
+        y = B.maxpool2x2(B.to_nhwc(x.cuda()).contiguous())
+        assert torch.equal(nchw(y), F.max_pool2d(x.float(), 2))
+        a, b = torch.randn(3, 4, 5, C).to(dt), torch.randn(3, 4, 5, C).to(dt)
+        assert torch.equal(B.add(a.cuda(), b.cuda()).cpu(), a + b)
+
+
+def test_errors_are_loud(B):
+    from approx.layers import MSCA
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        MSCA(8, 5, (7, 11, 21))(torch.randn(1, 8, 8, 8))
+    with pytest.raises(RuntimeError, match="cna_b200"):
+        B._check(B.lib().cna_conv_taps_forward(0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 0, 1, 1, 0, 0, 0, 0))

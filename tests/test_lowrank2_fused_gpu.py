@@ -1,0 +1,86 @@
+"""Parity of the fused tcgen05 scheme-2 kernel: against the oracle run in bf16 on identical bf16
+inputs/weights (tolerance compare4d <= 1e-3, BASELINE.json) and against the generic CUDA path."""
+import pytest
+import torch
+
+from oracle import approx_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # B, C, H, W, K, N, relu
+    (2, 64, 56, 56, 16, 64, False),     # config-1 style single layer
+    (2, 64, 56, 56, 64, 64, True),
+    (2, 3, 32, 30, 8, 64, False),       # first layer: C=3 padded to 16, K=8 padded to 16
+    (1, 128, 20, 37, 32, 128, True),    # ragged H/W: edge tiles clip
+    (2, 256, 14, 14, 64, 256, False),   # W=14: single column tile, 4 channel chunks
+    (1, 512, 14, 14, 64, 512, True),    # weights do not fit: streamed mode
+    (3, 96, 9, 5, 4, 192, False),       # C=96 -> CK=32, tiny image
+    (1, 48, 17, 15, 16, 64, False),     # C=48 -> CK=16 x 3 chunks
+]
+
+
+def make(C, K, N, seed):
+    g = torch.Generator().manual_seed(seed)
+    v_w = (torch.randn(K, C, 3, 1, generator=g) / (3 * C) ** 0.5).bfloat16()
+    h_w = (torch.randn(N, K, 1, 3, generator=g) / (3 * K) ** 0.5).bfloat16()
+    b = torch.randn(N, generator=g).bfloat16()
+    return v_w, h_w, b
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_fused_matches_bf16_oracle(case):
+    from approx import backend as B
+    Bn, C, H, W, K, N, relu = case
+    v_w, h_w, b = make(C, K, N, 11)
+    x = torch.randn(Bn, C, H, W, generator=torch.Generator().manual_seed(5)).bfloat16()
+    ref = O.lowrank2_forward(x, v_w, h_w, b, (1, 1), (1, 1))
+    if relu:
+        ref = torch.relu(ref)
+    assert B.lowrank2_fused_supported(H, W, C, K, N, 3)
+    wv, wh = B.lowrank2_pack(v_w.cuda().float(), h_w.cuda().float())
+    xn = B.to_nhwc(x.cuda(), B.round_up(C, 16))
+    y = B.lowrank2_fused(xn, wv, wh, b.float().cuda(), relu=relu)
+    torch.cuda.synchronize()
+    got = y.permute(0, 3, 1, 2).float().cpu()
+    err = O.compare4d(ref.float(), got)
+    assert err < 1e-3, f"rel err {err}"
+    # generic CUDA path (two tap-GEMM launches, T through HBM) must agree too
+    wv_g = B.pack_taps(v_w.cuda().float(), torch.bfloat16)
+    wh_g = B.pack_taps(h_w.cuda().float(), torch.bfloat16)
+    t = B.conv_taps(B.to_nhwc(x.cuda()), wv_g, None, K, 3, 0, (1, 1), 1)
+    y2 = B.conv_taps(t, wh_g, b.float().cuda(), N, 3, 1, (1, 1), 1, relu=relu)
+    assert O.compare4d(y2.permute(0, 3, 1, 2).float().cpu(), got) < 1e-3
+
+
+def test_module_takes_fused_path_and_matches_oracle():
+    from approx import backend as B
+    from approx.layers import LowRankExpConvV2
+    torch.manual_seed(0)
+    m = LowRankExpConvV2(64, 16, (3, 3), (1, 1), (1, 1), out_channels=128).cuda().bfloat16()
+    x = torch.randn(8, 64, 56, 56).bfloat16()
+    before = B.launch_count()
+    y = m(x.cuda())
+    assert B.launch_count() - before <= 3          # (layout) + pack + ONE fused conv kernel
+    ref = O.lowrank2_forward(x, m.v_conv.weight.cpu(), m.h_conv.weight.cpu(), m.h_conv.bias.cpu(), (1, 1), (1, 1))
+    assert y.shape == ref.shape
+    assert O.compare4d(ref.float(), y.float().cpu()) < 1e-3
+
+
+def test_linearity_at_full_size():
+    """Size-independent property at a BASELINE-sized layer: f(2x) - bias == 2(f(x) - bias) (exact in bf16
+    up to the final rounding: powers of two commute with every rounding step)."""
+    from approx import backend as B
+    C, K, N = 64, 64, 64
+    v_w, h_w, _ = make(C, K, N, 3)
+    wv, wh = B.lowrank2_pack(v_w.cuda().float(), h_w.cuda().float())
+    x = torch.randn(16, 224, 224, C, device="cuda").bfloat16()
+    y1 = B.lowrank2_fused(x, wv, wh, None)
+    y2 = B.lowrank2_fused(x * 2, wv, wh, None)
+    assert torch.equal(y2, y1 * 2)
+    # and a tile-boundary check against the generic path on a slice
+    wv_g = B.pack_taps(v_w.cuda().float(), torch.bfloat16)
+    wh_g = B.pack_taps(h_w.cuda().float(), torch.bfloat16)
+    t = B.conv_taps(x[:2].contiguous(), wv_g, None, K, 3, 0, (1, 1), 1)
+    yg = B.conv_taps(t, wh_g, None, N, 3, 1, (1, 1), 1)
+    assert O.compare4d(yg.permute(0, 3, 1, 2).float().cpu(), y1[:2].permute(0, 3, 1, 2).float().cpu()) < 1e-3

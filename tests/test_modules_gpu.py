@@ -1,0 +1,165 @@
+"""Drop-in modules and apps on the GPU against golden vectors produced by the reference's own modules
+(tests/golden/make_golden.py).  Weights are loaded through `load_state_dict` with the reference's keys,
+which also proves state_dict compatibility.  fp32 tolerance: compare4d < 1e-5."""
+import io
+import contextlib
+
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+from oracle import approx_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a)).float()
+
+
+def sd_from(g, prefix):
+    return {k[len(prefix):]: T(v) for k, v in g.items() if k.startswith(prefix) and "." in k[len(prefix):]}
+
+
+def test_lowrank2_shipped_golden(golden):
+    from approx.layers import LowRankExpConvV2
+    g = golden("lowrank2_shipped")
+    for tag in "ab":
+        C, K, kh, kw, sh, sw, ph, pw = (int(v) for v in g[f"{tag}_cfg"])
+        m = LowRankExpConvV2(C, K, (kh, kw), (sh, sw), (ph, pw))
+        m.load_state_dict(sd_from(g, f"{tag}_"), strict=True)
+        y = m.cuda()(T(g[f"{tag}_x"]).cuda())
+        assert O.compare4d(T(g[f"{tag}_y"]), y.cpu()) < TOL
+
+
+def test_lowrank1_golden_forward_and_decomp(golden):
+    from approx.layers import LowRankExpConvV1
+    g = golden("lowrank1")
+    for tag in "ab":
+        C, N, k, s, p, M = (int(v) for v in g[f"{tag}_cfg"])
+        m = LowRankExpConvV1(C, N, k, s, p, num_base=M)
+        sd = {kk: vv for kk, vv in sd_from(g, f"{tag}_").items() if not kk.startswith("dec_")}
+        m.load_state_dict(sd, strict=True)
+        m = m.cuda()
+        x = T(g[f"{tag}_x"]).cuda()
+        assert O.compare4d(T(g[f"{tag}_y"]), m(x).cpu()) < TOL
+        m.decomp()          # batched rank-1 SVD on the device
+        m.decomp()          # idempotent
+        assert sorted(m.state_dict()) == sorted(k[len(f"{tag}_dec_"):] for k in g if k.startswith(f"{tag}_dec_"))
+        assert O.compare4d(T(g[f"{tag}_y_decomp"]), m(x).cpu()) < TOL
+
+
+def test_lowrank_exp_v1_app_golden(golden):
+    from approx.core import LowRankExpV1
+    g = golden("lowrank1_app")
+    src = nn.Conv2d(6, 10, 3, 1, 1)
+    src.weight.data = T(g["src_weight"]); src.bias.data = T(g["src_bias"])
+    app = LowRankExpV1(num_bases=(4,), max_iter=0, lmda_length=1, min_lmda=0.001, max_lmda=0.001,
+                       init_method="svd", do_decomp=True)
+    sub = app.initialize(src)              # weights still on the CPU, as in Runner.run
+    app.optimize(sub)                      # SVD fit runs on the device, results land back on the CPU
+    assert sub.new.s_conv.weight.device.type == "cpu"
+    C, M = 6, 4
+    recon = lambda sw, dw: dw.reshape(-1, M) @ sw.reshape(C, M, 9)[0]
+    assert torch.allclose(recon(sub.new.s_conv.weight.data, sub.new.d_conv.weight.data),
+                          recon(T(g["fit_s_conv.weight"]), T(g["fit_d_conv.weight"])), atol=2e-5)
+    tgt = app.postprocess(sub).cuda()
+    assert sorted(tgt.state_dict()) == sorted(k[len("post_"):] for k in g if k.startswith("post_"))
+    y = tgt(T(g["x"]).cuda())
+    assert O.compare4d(T(g["y_post"]), y.cpu()) < 2e-5
+    with pytest.raises(NotImplementedError):
+        LowRankExpV1((4,), 10, 10, 0.001, 0.1).optimize(LowRankExpV1((4,), 10, 10, 0.001, 0.1).initialize(src))
+
+
+def _msca_from_golden(g):
+    from approx.layers import MSCA
+    m = MSCA(8, 5, (7, 11, 21))
+    m.load_state_dict(sd_from(g, "src_"), strict=True)
+    return m
+
+
+def test_msca_original_golden(golden):
+    g = golden("msca")
+    m = _msca_from_golden(g).cuda()
+    for t in ("big", "small"):
+        assert O.compare4d(T(g[f"y_src_{t}"]), m(T(g[f"x_{t}"]).cuda()).cpu()) < TOL
+
+
+def test_msca_equivalent_kernel_golden(golden):
+    from approx.core import MscaRep
+    g = golden("msca")
+    m = _msca_from_golden(g).cuda()
+    w, b, r = MscaRep.get_equivalent_kernel(m.sd_convs)
+    assert torch.allclose(w.cpu(), T(g["eq_weight"]), atol=1e-6)
+    assert torch.allclose(b.cpu(), T(g["eq_bias"]), atol=1e-6)
+    assert torch.allclose(r.cpu(), T(g["eq_res"]), atol=1e-6)
+
+
+@pytest.mark.parametrize("decomp,fix", [(0, True), (0, False), (1, True), (2, True), (4, True), (3, False)])
+def test_msca_rep_variants_golden(golden, decomp, fix):
+    from approx.core import MscaRep
+    g = golden("msca")
+    tag = f"d{decomp}{'f' if fix else 'n'}"
+    src = _msca_from_golden(g)                       # CPU weights, as in Runner.run
+    app = MscaRep(decomp=decomp, fix=fix)
+    sub = app.initialize(src)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        app.optimize(sub)
+    if decomp > 0:
+        assert abs(float(buf.getvalue().strip().rstrip(",")) - float(g[f"{tag}_pce"])) < 1e-4
+    tgt = app.postprocess(sub)
+    want_keys = sorted(k[len(tag) + 1:] for k in g if k.startswith(tag + "_") and "." in k)
+    assert sorted(tgt.state_dict()) == want_keys
+    tgt = tgt.cuda()
+    for t in ("big", "small"):
+        y = tgt(T(g[f"x_{t}"]).cuda())
+        assert O.compare4d(T(g[f"{tag}_y_{t}"]), y.cpu()) < 3e-5, (tag, t)
+    if (decomp, fix) in ((0, True), (4, True)):       # exact re-parameterisations reproduce the source block
+        for t in ("big", "small"):
+            assert O.compare4d(T(g[f"y_src_{t}"]), tgt(T(g[f"x_{t}"]).cuda()).cpu()) < 3e-5
+
+
+def test_msca_profile_app_and_substitution(golden):
+    from approx.core import MscaProfile
+    from approx.layers import MSCAProfile, Substitution
+    g = golden("msca")
+    src = _msca_from_golden(g)
+    sub = MscaProfile(deploy=False).initialize(src)
+    assert isinstance(sub, Substitution) and isinstance(sub.new, MSCAProfile)
+    sub = sub.cuda()
+    x = T(g["x_big"]).cuda()
+    y_old = sub(x)
+    sub.switch_new(remove_old=True)
+    assert not hasattr(sub, "old")
+    assert O.compare4d(y_old.cpu(), sub(x).cpu()) < TOL
+    assert O.compare4d(T(g["y_src_big"]), sub(x).cpu()) < TOL
+
+
+def test_svd_small_reconstruction():
+    from approx import backend as B
+    torch.manual_seed(0)
+    for shape in [(37, 1, 3, 3), (5, 21, 21), (3, 8, 5), (2, 5, 8), (4, 25, 25)]:
+        A = torch.randn(*shape)
+        U, S, Vh = B.svd_small(A.cuda())
+        rec = (U * S.unsqueeze(-2)) @ Vh
+        assert torch.allclose(rec.cpu(), A, atol=2e-5)
+        assert torch.allclose(S.cpu(), torch.linalg.svdvals(A), atol=2e-5)
+        assert bool((S[..., :-1] >= S[..., 1:] - 1e-6).all())
+
+
+def test_bf16_msca_against_bf16_oracle(golden):
+    """bf16 mode: the kernels round where the reference's bf16 modules materialise tensors."""
+    g = golden("msca")
+    m = _msca_from_golden(g)
+    x = T(g["x_big"]).bfloat16()
+    mb = _msca_from_golden(g).bfloat16()
+    sd = {k: v for k, v in mb.state_dict().items()}
+    br = [tuple(sd[f"sd_convs.branches.{i}.{n}"] for n in ("conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias"))
+          for i in range(3)]
+    ref = O.msca_forward(x, sd["conv0.weight"], sd["conv0.bias"], lambda a: O.parallel_forward(a, br, True),
+                         sd["channel_mix.weight"], sd["channel_mix.bias"])
+    y = mb.cuda()(x.cuda())
+    assert O.compare4d(ref.float(), y.float().cpu()) < 3e-3

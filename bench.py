@@ -132,8 +132,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / max(1, args.steps) * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"vgg16_trunk_scheme2_rank{args.rank}_b{sample}x224x224_cpu_sample", "rank": args.rank,
-                   "batch_per_step": sample},
+        "config": {"workload": f"vgg16_trunk_scheme2_rank{args.rank}_b{args.batch}x224x224_bf16", "rank": args.rank,
+                   "batch_per_gpu": args.batch, "layers": 13, "cpu_sample_batch": sample},
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
                          "sample": f"{max(1, args.steps)} passes of {sample} images through the 13-layer trunk, fp32, torch CPU"},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -263,6 +263,13 @@ def run_ours(args):
                          "fused_conv_share_of_step": conv_ms / ms},
             "clocks": clocks,
         }
+        if args.per_layer:
+            for i, (C, N, H) in enumerate(VGG):
+                lms = sum(ev[s_][i][0].elapsed_time(ev[s_][i][1]) for s_ in range(args.steps)) / args.steps
+                lb = (2 * H * H * (C + N) + 6 * K * (C + N) + 2 * N) * Bsz
+                lf = (6 * H * H * K * (C + N)) * Bsz
+                sys.stderr.write(f"layer {i + 1:2d} {C:3d}->{N:3d} @{H:3d}: {lms:7.3f} ms  {lb / lms / 1e6:7.0f} GB/s "
+                                 f"({lb / lms / 1e6 / hbm_peak:5.1%} of HBM peak)  {lf / lms / 1e9:6.0f} TFLOP/s\n")
         if world == 1 and not args.no_cpu:
             ips, threads, dt = cpu_reference_run(K, 4, 3, 1)
             line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
@@ -281,6 +288,7 @@ def main():
     ap.add_argument("--rank", type=int, default=64)
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--per-layer", action="store_true", help="print per-layer time / GB/s to stderr")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

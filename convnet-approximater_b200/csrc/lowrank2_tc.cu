@@ -37,7 +37,7 @@
 namespace cna {
 using namespace ptx;
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;        // warp 0 TMA, warp 1 MMA, warps 2-5 T-epilogue, warps 6-9 Y-epilogue
 constexpr int kTileRows = 8;           // output rows per tile
 constexpr int kTileCols = 16;          // computed columns per tile (14 valid + 2 halo)
 constexpr int kValidCols = kTileCols - 2;
@@ -45,16 +45,20 @@ constexpr int kXRows = kTileRows + 2;  // x rows per tile (d = 3)
 constexpr int kTCols = kTileCols + 2;  // T columns kept in smem
 constexpr int kNT = 64;                // GEMM2 N-tile (output channels per accumulator)
 constexpr int kTmemCols = 256;
-constexpr int kMaxStages = 4;
+constexpr int kMaxStages = 6;
 constexpr int kMaxNTiles = 16;         // N <= 1024
+// T lives in the NO-swizzle K-major UMMA layout: 8-slot groups of 16-byte chunks, group pitch kTSbo, chunk-plane
+// pitch kTLbo.  The 144-byte group pitch (instead of 128) makes the transposing epilogue stores — 8 lanes that
+// hit 8 consecutive groups at the same in-group row — fall into 8 different bank quads.
+constexpr uint32_t kTSbo = 144;
+constexpr uint32_t kTLbo = kTCols * kTSbo;   // 2592
 
 struct LR2Params {
     int B, H, W, N;
-    int CK, KP;            // channel chunk (16/32/64), padded rank (16/32/64)
     int nch;               // number of channel chunks = c_pad / CK
     int nnt;               // N / 64
     int tiles_w, tiles_h;  // tile grid per image
-    long long ntiles;
+    int ntiles;
     int stages;            // x ring depth
     int resident;          // 1: all weights stay in smem for the whole kernel; 0: streamed per tile
     int relu;
@@ -67,12 +71,7 @@ struct LR2Params {
     uint32_t off_bias, off_bar;
 };
 
-__device__ __forceinline__ uint32_t swz_type(int row_bytes) { return row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u); }
-// canonical Swizzle<B,4,3> on a byte offset relative to a 1024-aligned base
-__device__ __forceinline__ uint32_t swz_off(uint32_t off, int row_bytes) {
-    uint32_t mask = row_bytes == 128 ? 7u : (row_bytes == 64 ? 3u : 1u);
-    return off ^ (((off >> 7) & mask) << 4);
-}
+__host__ __device__ constexpr uint32_t swz_type(int row_bytes) { return row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u); }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
@@ -80,6 +79,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ float4 ld_shared_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
 // barrier indices (each 8 bytes) inside the barrier block
 enum : int {
@@ -97,10 +97,28 @@ enum : int {
     BAR_COUNT = BAR_YACC_EMPTY + 2
 };
 
+// 64-bit UMMA shared-memory descriptor with the start-address field left 0; add (addr >> 4) per operand.
+__host__ __device__ constexpr uint64_t desc_hi(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+    return ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)(layout_type & 7) << 61);
+}
+
+struct TileCoord { int b, h0, w0; };
+__device__ __forceinline__ TileCoord decode_tile(int tile, const LR2Params& p) {
+    int per_img = p.tiles_w * p.tiles_h;
+    int b = tile / per_img, rem = tile - b * per_img;
+    int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
+    return {b, th * kTileRows, tw * kValidCols};
+}
+
+template <int CK, int KP>
 __global__ void __launch_bounds__(kThreads, 1)
 lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_wv,
                       const __grid_constant__ CUtensorMap tm_wh, const __grid_constant__ CUtensorMap tm_y,
                       const float* __restrict__ bias, const LR2Params p) {
+    constexpr int XROW = CK * 2;            // bytes per x / Wv smem row (== swizzle span)
+    constexpr int HROW = KP * 2;            // bytes per Wh smem row
+    constexpr int TCH = KP / 8;             // 16-byte chunks per T slot
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -110,8 +128,6 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + p.off_bar + 8 * BAR_COUNT);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int xrow_b = p.CK * 2;   // bytes per x / Wv smem row
-    const int trow_b = p.KP * 2;   // bytes per T / Wh smem row
 
     // ---------------- one-time setup ----------------
     if (warp == 0 && lane == 0) {
@@ -128,14 +144,10 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     }
     if (warp == 1) tmem_alloc<kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
     for (int i = threadIdx.x; i < p.N; i += kThreads) sbias[i] = bias ? bias[i] : 0.f;
-    // T columns 0 and 17 are never produced (they only feed the two discarded halo outputs): keep them finite.
-    for (int i = threadIdx.x; i < 2 * 2 * kTileRows * trow_b / 16; i += kThreads) {
-        int per_buf = 2 * kTileRows * trow_b / 16;
-        int bsel = i / per_buf, j = i % per_buf;
-        int slot = j / (trow_b / 16);                              // 0..15 -> slots 0..7 and 136..143
-        int ch = j % (trow_b / 16);
-        int s = slot < kTileRows ? slot : (kTCols - 1) * kTileRows + (slot - kTileRows);
-        st_shared_v4(base + p.off_t + bsel * p.t_buf + s * trow_b + ch * 16, 0, 0, 0, 0);
+    // T column groups 0 and 17 are never produced (they only feed the two discarded halo outputs): keep them finite.
+    for (int i = threadIdx.x; i < 2 * 2 * TCH * 8; i += kThreads) {
+        int row = i & 7, ch = (i >> 3) % TCH, g = ((i >> 3) / TCH) & 1, bsel = (i >> 3) / TCH / 2;
+        st_shared_v4(base + p.off_t + bsel * p.t_buf + ch * kTLbo + (g ? (kTCols - 1) : 0) * kTSbo + row * 16, 0, 0, 0, 0);
     }
     fence_proxy_async_smem();
     tc_fence_before_sync();
@@ -145,54 +157,51 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     const uint32_t tmem_T = tmem;            // + buf*64
     const uint32_t tmem_Y = tmem + 128;      // + buf*64
 
-    const long long first = blockIdx.x, step = gridDim.x;
-    const long long my_tiles = first < p.ntiles ? (p.ntiles - first + step - 1) / step : 0;
-    const int tiles_per_img = p.tiles_w * p.tiles_h;
+    const int first = blockIdx.x, step = gridDim.x;
+    const int my_tiles = first < p.ntiles ? (p.ntiles - first + step - 1) / step : 0;
 
     if (warp == 0) {
         // =========================== TMA producer ===========================
         if (lane == 0 && my_tiles > 0) {
-            const uint32_t x_bytes = (uint32_t)(kXRows * kTileCols * xrow_b);
-            const uint32_t v_bytes = (uint32_t)(3 * p.KP * xrow_b);
-            const uint32_t h_bytes = (uint32_t)(3 * kNT * trow_b);
+            constexpr uint32_t x_bytes = kXRows * kTileCols * XROW;
+            constexpr uint32_t v_bytes = 3 * KP * XROW;
+            constexpr uint32_t h_bytes = 3 * kNT * HROW;
             if (p.resident) {
                 mbar_arrive_expect_tx(bar(BAR_WFULL), v_bytes * p.nch + h_bytes * p.nnt);
                 for (int ch = 0; ch < p.nch; ++ch)
-                    tma_load_2d(base + p.off_v + ch * p.v_chunk, &tm_wv, bar(BAR_WFULL), ch * p.CK, 0);
+                    tma_load_2d(base + p.off_v + ch * p.v_chunk, &tm_wv, bar(BAR_WFULL), ch * CK, 0);
                 for (int nt = 0; nt < p.nnt; ++nt)
                     for (int dx = 0; dx < 3; ++dx)
-                        tma_load_2d(base + p.off_h + nt * p.h_tile + dx * (kNT * trow_b), &tm_wh, bar(BAR_WFULL), 0,
+                        tma_load_2d(base + p.off_h + nt * p.h_tile + dx * (kNT * HROW), &tm_wh, bar(BAR_WFULL), 0,
                                     dx * p.N + nt * kNT);
             }
-            long long kx = 0, qh = 0;  // global x-chunk / Wh-tile counters
-            auto load_x = [&](long long it) {
-                long long tile = first + it * step;
-                int b = (int)(tile / tiles_per_img);
-                int rem = (int)(tile % tiles_per_img);
-                int h0 = (rem / p.tiles_w) * kTileRows, w0 = (rem % p.tiles_w) * kValidCols;
-                for (int ch = 0; ch < p.nch; ++ch, ++kx) {
-                    int s = (int)(kx % p.stages);
-                    mbar_wait(bar(BAR_XEMPTY + s), (uint32_t)((kx / p.stages) & 1) ^ 1u);
-                    mbar_arrive_expect_tx(bar(BAR_XFULL + s), x_bytes + (p.resident ? 0u : v_bytes));
-                    tma_load_4d(base + p.off_x + s * p.x_stage, &tm_x, bar(BAR_XFULL + s), ch * p.CK, w0 - 1, h0 - 1, b);
+            int xs = 0; uint32_t xph = 0;   // x ring stage / phase
+            int hs = 0; uint32_t hph = 0;   // Wh ring stage / phase
+            auto load_x = [&](int it) {
+                TileCoord t = decode_tile(first + it * step, p);
+                for (int ch = 0; ch < p.nch; ++ch) {
+                    mbar_wait(bar(BAR_XEMPTY + xs), xph ^ 1u);
+                    mbar_arrive_expect_tx(bar(BAR_XFULL + xs), x_bytes + (p.resident ? 0u : v_bytes));
+                    tma_load_4d(base + p.off_x + xs * p.x_stage, &tm_x, bar(BAR_XFULL + xs), ch * CK, t.w0 - 1, t.h0 - 1, t.b);
                     if (!p.resident)
-                        tma_load_2d(base + p.off_v + s * p.v_chunk, &tm_wv, bar(BAR_XFULL + s), ch * p.CK, 0);
+                        tma_load_2d(base + p.off_v + xs * p.v_chunk, &tm_wv, bar(BAR_XFULL + xs), ch * CK, 0);
+                    if (++xs == p.stages) { xs = 0; xph ^= 1u; }
                 }
             };
             auto load_h = [&]() {
                 if (p.resident) return;
-                for (int nt = 0; nt < p.nnt; ++nt, ++qh) {
-                    int s = (int)(qh & 1);
-                    mbar_wait(bar(BAR_HEMPTY + s), (uint32_t)((qh >> 1) & 1) ^ 1u);
-                    mbar_arrive_expect_tx(bar(BAR_HFULL + s), h_bytes);
+                for (int nt = 0; nt < p.nnt; ++nt) {
+                    mbar_wait(bar(BAR_HEMPTY + hs), hph ^ 1u);
+                    mbar_arrive_expect_tx(bar(BAR_HFULL + hs), h_bytes);
                     for (int dx = 0; dx < 3; ++dx)
-                        tma_load_2d(base + p.off_h + s * p.h_tile + dx * (kNT * trow_b), &tm_wh, bar(BAR_HFULL + s), 0,
+                        tma_load_2d(base + p.off_h + hs * p.h_tile + dx * (kNT * HROW), &tm_wh, bar(BAR_HFULL + hs), 0,
                                     dx * p.N + nt * kNT);
+                    if (++hs == 2) { hs = 0; hph ^= 1u; }
                 }
             };
             // same order as the MMA warp consumes: x(0) | x(1) h(0) | x(2) h(1) | ...
             load_x(0);
-            for (long long it = 0; it < my_tiles; ++it) {
+            for (int it = 0; it < my_tiles; ++it) {
                 if (it + 1 < my_tiles) load_x(it + 1);
                 load_h();
             }
@@ -200,147 +209,151 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
         if (lane == 0 && my_tiles > 0) {
-            const uint32_t idesc1 = umma_idesc_bf16(128, (uint32_t)p.KP);
-            const uint32_t idesc2 = umma_idesc_bf16(128, (uint32_t)kNT);
-            const uint32_t xs = swz_type(xrow_b), ts = swz_type(trow_b);
-            const int kk1 = p.CK / 16, kk2 = p.KP / 16;
-            long long kx = 0, q = 0;
+            constexpr uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KP >> 3) << 17) | (8u << 24);
+            constexpr uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kNT >> 3) << 17) | (8u << 24);
+            constexpr uint64_t xdesc = desc_hi(16, 8 * XROW, swz_type(XROW));     // x tile and Wv chunk (swizzled, K-major)
+            constexpr uint64_t hdesc = desc_hi(16, 8 * HROW, swz_type(HROW));     // Wh tile
+            constexpr uint64_t tdesc = desc_hi(kTLbo, kTSbo, 0);                  // T: no-swizzle K-major
+            int xs = 0; uint32_t xph = 0;
+            int q = 0;   // N-tile counter (Y accumulator / Wh ring index)
             if (p.resident) { mbar_wait(bar(BAR_WFULL), 0); tc_fence_after_sync(); }
-            auto gemm1 = [&](long long it) {
-                int buf = (int)(it & 1);
+            auto gemm1 = [&](int it) {
+                const int buf = it & 1;
                 mbar_wait(bar(BAR_TACC_EMPTY + buf), (uint32_t)((it >> 1) & 1) ^ 1u);
                 tc_fence_after_sync();
-                for (int ch = 0; ch < p.nch; ++ch, ++kx) {
-                    int s = (int)(kx % p.stages);
-                    mbar_wait(bar(BAR_XFULL + s), (uint32_t)((kx / p.stages) & 1));
+                const uint32_t d = tmem_T + buf * 64;
+                for (int ch = 0; ch < p.nch; ++ch) {
+                    mbar_wait(bar(BAR_XFULL + xs), xph);
                     tc_fence_after_sync();
-                    uint32_t a0 = base + p.off_x + s * p.x_stage;
-                    uint32_t b0 = base + p.off_v + (p.resident ? ch : s) * p.v_chunk;
+                    const uint64_t a0 = xdesc + ((base + p.off_x + xs * p.x_stage) >> 4);
+                    const uint64_t b0 = xdesc + ((base + p.off_v + (p.resident ? ch : xs) * p.v_chunk) >> 4);
+#pragma unroll
                     for (int dy = 0; dy < 3; ++dy)
-                        for (int kk = 0; kk < kk1; ++kk) {
-                            uint64_t ad = umma_desc(a0 + dy * kTileCols * xrow_b + kk * 32, 8 * xrow_b, xs);
-                            uint64_t bd = umma_desc(b0 + dy * p.KP * xrow_b + kk * 32, 8 * xrow_b, xs);
-                            umma_bf16(tmem_T + buf * 64, ad, bd, idesc1, (ch | dy | kk) != 0);
-                        }
-                    umma_commit(bar(BAR_XEMPTY + s));
+#pragma unroll
+                        for (int kk = 0; kk < CK / 16; ++kk)
+                            umma_bf16(d, a0 + ((dy * kTileCols * XROW + kk * 32) >> 4), b0 + ((dy * KP * XROW + kk * 32) >> 4),
+                                      idesc1, (uint32_t)((ch | dy | kk) != 0));
+                    umma_commit(bar(BAR_XEMPTY + xs));
+                    if (++xs == p.stages) { xs = 0; xph ^= 1u; }
                 }
                 umma_commit(bar(BAR_TACC_FULL + buf));
             };
-            auto gemm2 = [&](long long j) {
-                int buf = (int)(j & 1);
+            auto gemm2 = [&](int j) {
+                const int buf = j & 1;
                 mbar_wait(bar(BAR_TSM_FULL + buf), (uint32_t)((j >> 1) & 1));
                 tc_fence_after_sync();
-                uint32_t a0 = base + p.off_t + buf * p.t_buf;
+                const uint64_t a0 = tdesc + ((base + p.off_t + buf * p.t_buf) >> 4);
                 for (int nt = 0; nt < p.nnt; ++nt, ++q) {
-                    int yb = (int)(q & 1);
-                    mbar_wait(bar(BAR_YACC_EMPTY + yb), (uint32_t)((q >> 1) & 1) ^ 1u);
-                    uint32_t b0;
+                    const int yb = q & 1;
+                    const uint32_t ph = (uint32_t)((q >> 1) & 1);
+                    mbar_wait(bar(BAR_YACC_EMPTY + yb), ph ^ 1u);
+                    uint32_t hb;
                     if (p.resident) {
-                        b0 = base + p.off_h + nt * p.h_tile;
+                        hb = base + p.off_h + nt * p.h_tile;
                     } else {
-                        mbar_wait(bar(BAR_HFULL + yb), (uint32_t)((q >> 1) & 1));
-                        b0 = base + p.off_h + yb * p.h_tile;
+                        mbar_wait(bar(BAR_HFULL + yb), ph);
+                        hb = base + p.off_h + yb * p.h_tile;
                     }
                     tc_fence_after_sync();
+                    const uint64_t b0 = hdesc + (hb >> 4);
+                    const uint32_t d = tmem_Y + yb * 64;
+#pragma unroll
                     for (int dx = 0; dx < 3; ++dx)
-                        for (int kk = 0; kk < kk2; ++kk) {
-                            uint64_t ad = umma_desc(a0 + dx * kTileRows * trow_b + kk * 32, 8 * trow_b, ts);
-                            uint64_t bd = umma_desc(b0 + dx * (kNT * trow_b) + kk * 32, 8 * trow_b, ts);
-                            umma_bf16(tmem_Y + yb * 64, ad, bd, idesc2, (dx | kk) != 0);
-                        }
+#pragma unroll
+                        for (int kk = 0; kk < KP / 16; ++kk)
+                            umma_bf16(d, a0 + ((dx * kTSbo + kk * 2 * kTLbo) >> 4), b0 + ((dx * (kNT * HROW) + kk * 32) >> 4),
+                                      idesc2, (uint32_t)((dx | kk) != 0));
                     if (!p.resident) umma_commit(bar(BAR_HEMPTY + yb));
                     umma_commit(bar(BAR_YACC_FULL + yb));
                 }
                 umma_commit(bar(BAR_TSM_EMPTY + buf));
             };
             gemm1(0);
-            for (long long it = 0; it < my_tiles; ++it) {
+            for (int it = 0; it < my_tiles; ++it) {
                 if (it + 1 < my_tiles) gemm1(it + 1);
                 gemm2(it);
             }
         }
-    } else {
-        // =========================== epilogue warps ===========================
+    } else if (warp < 6) {
+        // =========================== T-epilogue warps (2..5) ===========================
+        // TMEM accumulator of GEMM1 -> bf16 -> shared memory, transposing slot order (row,col) -> (col,row).
         const int lg = warp & 3;                 // TMEM lane group this warp may access
-        const int m = lg * 32 + lane;            // accumulator row (UMMA M index)
+        const int m = lg * 32 + lane;            // accumulator row: m = r*16 + xc
         const uint32_t lane_addr = (uint32_t)(lg * 32) << 16;
-        const int et = (warp - 2) * 32 + lane;   // 0..127 index among epilogue threads
-        long long q = 0;
-        auto t_epilogue = [&](long long it) {
-            int buf = (int)(it & 1);
-            mbar_wait(bar(BAR_TACC_FULL + buf), (uint32_t)((it >> 1) & 1));
-            mbar_wait(bar(BAR_TSM_EMPTY + buf), (uint32_t)((it >> 1) & 1) ^ 1u);
+        const int r = m >> 4, xc = m & 15;
+        const uint32_t slot_off = (uint32_t)(xc + 1) * kTSbo + (uint32_t)r * 16;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int buf = it & 1;
+            const uint32_t ph = (uint32_t)((it >> 1) & 1);
+            mbar_wait(bar(BAR_TACC_FULL + buf), ph);
             tc_fence_after_sync();
-            // GEMM1 row order is (row, col): m = r*16 + xc.  T slot order is (col, row): (xc+1)*8 + r.
-            const int r = m >> 4, xc = m & 15;
-            const uint32_t row_off = (uint32_t)(((xc + 1) * kTileRows + r) * trow_b);
-            const uint32_t tb = base + p.off_t + buf * p.t_buf;
-            for (int c16 = 0; c16 < p.KP / 16; ++c16) {
-                uint32_t v[16];
-                tmem_ld16(tmem_T + buf * 64 + lane_addr + c16 * 16, v);
-                tmem_ld_wait();
-                uint32_t w[8];
+            uint32_t v[KP];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) w[i] = pack_bf16(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-                st_shared_v4(tb + swz_off(row_off + (c16 * 2) * 16, trow_b), w[0], w[1], w[2], w[3]);
-                st_shared_v4(tb + swz_off(row_off + (c16 * 2 + 1) * 16, trow_b), w[4], w[5], w[6], w[7]);
-            }
-            fence_proxy_async_smem();
+            for (int c16 = 0; c16 < KP / 16; ++c16) tmem_ld16(tmem_T + buf * 64 + lane_addr + c16 * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[c16 * 16]));
+            tmem_ld_wait();
             tc_fence_before_sync();
+            mbar_arrive(bar(BAR_TACC_EMPTY + buf));          // accumulator drained: GEMM1 of tile it+2 may start
+            mbar_wait(bar(BAR_TSM_EMPTY + buf), ph ^ 1u);     // GEMM2 of tile it-2 has finished reading this T buffer
+            const uint32_t tb = base + p.off_t + buf * p.t_buf + slot_off;
+#pragma unroll
+            for (int ch = 0; ch < TCH; ++ch)
+                st_shared_v4(tb + ch * kTLbo,
+                             pack_bf16(__uint_as_float(v[ch * 8 + 0]), __uint_as_float(v[ch * 8 + 1])),
+                             pack_bf16(__uint_as_float(v[ch * 8 + 2]), __uint_as_float(v[ch * 8 + 3])),
+                             pack_bf16(__uint_as_float(v[ch * 8 + 4]), __uint_as_float(v[ch * 8 + 5])),
+                             pack_bf16(__uint_as_float(v[ch * 8 + 6]), __uint_as_float(v[ch * 8 + 7])));
+            fence_proxy_async_smem();
             mbar_arrive(bar(BAR_TSM_FULL + buf));
-            mbar_arrive(bar(BAR_TACC_EMPTY + buf));
-        };
-        auto y_epilogue = [&](long long j) {
-            long long tile = first + j * step;
-            int b = (int)(tile / tiles_per_img);
-            int rem = (int)(tile % tiles_per_img);
-            int h0 = (rem / p.tiles_w) * kTileRows, w0 = (rem % p.tiles_w) * kValidCols;
-            // GEMM2 row order is (col, row): m = yc*8 + r ; staging order is the TMA box order (row, col, channel)
-            const int yc = m >> 3, r = m & 7;
-            const bool valid = yc >= 1 && yc <= kValidCols;
-            const uint32_t row_off = (uint32_t)((r * kValidCols + (yc - 1)) * 128);
+        }
+    } else {
+        // =========================== Y-epilogue warps (6..9) ===========================
+        // TMEM accumulator of GEMM2 -> +bias, ReLU -> bf16 -> swizzled staging -> TMA store.
+        const int lg = warp & 3;
+        const int m = lg * 32 + lane;            // accumulator row: m = yc*8 + r
+        const uint32_t lane_addr = (uint32_t)(lg * 32) << 16;
+        const int et = (warp - 6) * 32 + lane;   // 0..127
+        const int yc = m >> 3, r = m & 7;
+        const bool valid = yc >= 1 && yc <= kValidCols;
+        const uint32_t srow = (uint32_t)(r * kValidCols + (yc - 1));      // staging row (TMA box order: row, col)
+        const uint32_t row_off = srow * 128u, sw = srow & 7u;             // 128B-swizzle: chunk ^= row & 7
+        const float lo = p.relu ? 0.f : -INFINITY;
+        int q = 0;
+        for (int j = 0; j < my_tiles; ++j) {
+            TileCoord t = decode_tile(first + j * step, p);
             for (int nt = 0; nt < p.nnt; ++nt, ++q) {
-                int yb = (int)(q & 1);
+                const int yb = q & 1;
                 const uint32_t sb = base + p.off_y + yb * p.y_buf;
                 mbar_wait(bar(BAR_YACC_FULL + yb), (uint32_t)((q >> 1) & 1));
                 tc_fence_after_sync();
+                uint32_t v[kNT];
+#pragma unroll
+                for (int c16 = 0; c16 < kNT / 16; ++c16) tmem_ld16(tmem_Y + yb * 64 + lane_addr + c16 * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[c16 * 16]));
+                tmem_ld_wait();
+                tc_fence_before_sync();
+                mbar_arrive(bar(BAR_YACC_EMPTY + yb));       // accumulator drained: next N-tile's GEMM2 may start
                 // staging buffer yb was handed to a TMA store two N-tiles ago: wait until it has been read
                 if (et == 0) tma_store_wait_read<1>();
                 named_bar_sync(1, 128);
+                if (valid) {
+                    const float* bz = sbias + nt * kNT;
 #pragma unroll
-                for (int c16 = 0; c16 < kNT / 16; ++c16) {
-                    uint32_t v[16];
-                    tmem_ld16(tmem_Y + yb * 64 + lane_addr + c16 * 16, v);
-                    tmem_ld_wait();
-                    if (valid) {
-                        uint32_t w[8];
-                        const float* bz = sbias + nt * kNT + c16 * 16;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            float a = __uint_as_float(v[2 * i]) + bz[2 * i];
-                            float c = __uint_as_float(v[2 * i + 1]) + bz[2 * i + 1];
-                            if (p.relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
-                            w[i] = pack_bf16(a, c);
-                        }
-                        st_shared_v4(sb + swz_off(row_off + (c16 * 2) * 16, 128), w[0], w[1], w[2], w[3]);
-                        st_shared_v4(sb + swz_off(row_off + (c16 * 2 + 1) * 16, 128), w[4], w[5], w[6], w[7]);
+                    for (int ch = 0; ch < kNT / 8; ++ch) {
+                        float4 b0 = ld_shared_f4(bz + ch * 8), b1 = ld_shared_f4(bz + ch * 8 + 4);
+                        uint32_t w0 = pack_bf16(fmaxf(__uint_as_float(v[ch * 8 + 0]) + b0.x, lo), fmaxf(__uint_as_float(v[ch * 8 + 1]) + b0.y, lo));
+                        uint32_t w1 = pack_bf16(fmaxf(__uint_as_float(v[ch * 8 + 2]) + b0.z, lo), fmaxf(__uint_as_float(v[ch * 8 + 3]) + b0.w, lo));
+                        uint32_t w2 = pack_bf16(fmaxf(__uint_as_float(v[ch * 8 + 4]) + b1.x, lo), fmaxf(__uint_as_float(v[ch * 8 + 5]) + b1.y, lo));
+                        uint32_t w3 = pack_bf16(fmaxf(__uint_as_float(v[ch * 8 + 6]) + b1.z, lo), fmaxf(__uint_as_float(v[ch * 8 + 7]) + b1.w, lo));
+                        st_shared_v4(sb + row_off + (((uint32_t)ch ^ sw) << 4), w0, w1, w2, w3);
                     }
                 }
-                tc_fence_before_sync();
-                mbar_arrive(bar(BAR_YACC_EMPTY + yb));
                 fence_proxy_async_smem();
                 named_bar_sync(2, 128);
                 if (et == 0) {
-                    tma_store_4d(&tm_y, sb, nt * kNT, w0, h0, b);
+                    tma_store_4d(&tm_y, sb, nt * kNT, t.w0, t.h0, t.b);
                     tma_store_commit();
                 }
             }
-        };
-        for (long long it = 0; it < my_tiles; ++it) {
-            t_epilogue(it);
-            if (it > 0) y_epilogue(it - 1);
         }
-        if (my_tiles > 0) y_epilogue(my_tiles - 1);
         if (et == 0) tma_store_wait_all<0>();
     }
 
@@ -412,12 +425,12 @@ static int pick_ck(int c_pad) { return c_pad % 64 == 0 ? 64 : (c_pad % 32 == 0 ?
 static uint32_t up1k(uint32_t v) { return (v + 1023u) & ~1023u; }
 
 // Fills the smem plan; returns total dynamic smem bytes (incl. 1 KB alignment slack) or 0 if it cannot fit.
-static size_t plan_smem(LR2Params& p, int c_pad, size_t limit) {
-    const uint32_t xrow = p.CK * 2, trow = p.KP * 2;
+static size_t plan_smem(LR2Params& p, int CK, int KP, size_t limit) {
+    const uint32_t xrow = CK * 2, trow = KP * 2;
     p.x_stage = up1k(kXRows * kTileCols * xrow);
-    p.v_chunk = up1k(3 * p.KP * xrow);
+    p.v_chunk = up1k(3 * KP * xrow);
     p.h_tile = up1k(3 * kNT * trow);
-    p.t_buf = up1k(kTCols * kTileRows * trow);
+    p.t_buf = up1k((KP / 8) * kTLbo);
     p.y_buf = 16384;
     const uint32_t fixed = 2 * p.t_buf + 2 * p.y_buf + up1k(p.N * 4) + 1024 /*barriers*/ + 1024 /*align slack*/;
     for (int resident = 1; resident >= 0; --resident) {
@@ -457,8 +470,9 @@ extern "C" {
 int cna_lowrank2_fused_supported(int H, int W, int c_pad, int k_pad, int N, int d) {
     if (!shape_ok(H, W, c_pad, k_pad, N, d)) return 0;
     LR2Params p{};
-    p.N = N; p.CK = pick_ck(c_pad); p.KP = k_pad; p.nch = c_pad / p.CK; p.nnt = N / kNT;
-    return plan_smem(p, c_pad, 227 * 1024) != 0 ? 1 : 0;
+    int CK = pick_ck(c_pad);
+    p.N = N; p.nch = c_pad / CK; p.nnt = N / kNT;
+    return plan_smem(p, CK, k_pad, 227 * 1024) != 0 ? 1 : 0;
 }
 
 int cna_lowrank2_pack(const float* v_w, const float* h_w, void* wv_packed, void* wh_packed, int C, int K, int N, int d,
@@ -485,28 +499,30 @@ int cna_lowrank2_fused_forward(const void* x, const void* wv_packed, const void*
         CNA_CUDA(cudaGetDevice(&dev));
         CNA_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
         CNA_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-        CNA_CUDA(cudaFuncSetAttribute(lowrank2_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     }
+    const int CK = pick_ck(c_pad);
     LR2Params p{};
     p.B = B; p.H = H; p.W = W; p.N = N; p.relu = relu;
-    p.CK = pick_ck(c_pad); p.KP = k_pad; p.nch = c_pad / p.CK; p.nnt = N / kNT;
+    p.nch = c_pad / CK; p.nnt = N / kNT;
     p.tiles_w = ceil_div(W, kValidCols); p.tiles_h = ceil_div(H, kTileRows);
-    p.ntiles = (long long)B * p.tiles_w * p.tiles_h;
-    size_t smem = plan_smem(p, c_pad, (size_t)max_smem);
+    long long ntiles = (long long)B * p.tiles_w * p.tiles_h;
+    CNA_CHECK(ntiles < (1LL << 31), "too many tiles for one launch");
+    p.ntiles = (int)ntiles;
+    size_t smem = plan_smem(p, CK, k_pad, (size_t)max_smem);
     CNA_CHECK(smem != 0, "shared-memory plan does not fit");
 
     CUtensorMap tm_x, tm_wv, tm_wh, tm_y;
     {
         cuuint64_t dims[4] = {(cuuint64_t)c_pad, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
         cuuint64_t str[3] = {(cuuint64_t)c_pad * 2, (cuuint64_t)W * c_pad * 2, (cuuint64_t)H * W * c_pad * 2};
-        cuuint32_t box[4] = {(cuuint32_t)p.CK, kTileCols, kXRows, 1};
-        if (encode(&tm_x, x, 4, dims, str, box, swizzle_for(p.CK * 2))) return 1;
+        cuuint32_t box[4] = {(cuuint32_t)CK, kTileCols, kXRows, 1};
+        if (encode(&tm_x, x, 4, dims, str, box, swizzle_for(CK * 2))) return 1;
     }
     {
         cuuint64_t dims[2] = {(cuuint64_t)c_pad, (cuuint64_t)3 * k_pad};
         cuuint64_t str[1] = {(cuuint64_t)c_pad * 2};
-        cuuint32_t box[2] = {(cuuint32_t)p.CK, (cuuint32_t)(3 * k_pad)};
-        if (encode(&tm_wv, wv_packed, 2, dims, str, box, swizzle_for(p.CK * 2))) return 1;
+        cuuint32_t box[2] = {(cuuint32_t)CK, (cuuint32_t)(3 * k_pad)};
+        if (encode(&tm_wv, wv_packed, 2, dims, str, box, swizzle_for(CK * 2))) return 1;
     }
     {
         cuuint64_t dims[2] = {(cuuint64_t)k_pad, (cuuint64_t)3 * N};
@@ -520,8 +536,29 @@ int cna_lowrank2_fused_forward(const void* x, const void* wv_packed, const void*
         cuuint32_t box[4] = {kNT, kValidCols, kTileRows, 1};
         if (encode(&tm_y, y, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     }
-    int grid = (int)std::min<long long>(p.ntiles, num_sms);
-    lowrank2_fused_kernel<<<grid, kThreads, smem, as_stream(stream)>>>(tm_x, tm_wv, tm_wh, tm_y, bias, p);
+    int grid = std::min(p.ntiles, num_sms);
+    cudaStream_t st = as_stream(stream);
+#define CNA_LR2_LAUNCH(CKV, KPV)                                                                                         \
+    do {                                                                                                                 \
+        static bool attr_set = false;                                                                                    \
+        if (!attr_set) {                                                                                                 \
+            CNA_CUDA(cudaFuncSetAttribute(lowrank2_fused_kernel<CKV, KPV>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                          max_smem));                                                                    \
+            attr_set = true;                                                                                             \
+        }                                                                                                                \
+        lowrank2_fused_kernel<CKV, KPV><<<grid, kThreads, smem, st>>>(tm_x, tm_wv, tm_wh, tm_y, bias, p);                 \
+    } while (0)
+#define CNA_LR2_DISPATCH_KP(CKV)                                       \
+    do {                                                               \
+        if (k_pad == 16) CNA_LR2_LAUNCH(CKV, 16);                      \
+        else if (k_pad == 32) CNA_LR2_LAUNCH(CKV, 32);                 \
+        else CNA_LR2_LAUNCH(CKV, 64);                                  \
+    } while (0)
+    if (CK == 16) CNA_LR2_DISPATCH_KP(16);
+    else if (CK == 32) CNA_LR2_DISPATCH_KP(32);
+    else CNA_LR2_DISPATCH_KP(64);
+#undef CNA_LR2_DISPATCH_KP
+#undef CNA_LR2_LAUNCH
     CNA_LAUNCH_OK();
     return 0;
 }

@@ -162,11 +162,11 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
 
     if (warp == 0) {
         // =========================== TMA producer ===========================
-        if (lane == 0 && my_tiles > 0) {
+        if (my_tiles > 0) {
             constexpr uint32_t x_bytes = kXRows * kTileCols * XROW;
             constexpr uint32_t v_bytes = 3 * KP * XROW;
             constexpr uint32_t h_bytes = 3 * kNT * HROW;
-            if (p.resident) {
+            if (p.resident && elect_one()) {
                 mbar_arrive_expect_tx(bar(BAR_WFULL), v_bytes * p.nch + h_bytes * p.nnt);
                 for (int ch = 0; ch < p.nch; ++ch)
                     tma_load_2d(base + p.off_v + ch * p.v_chunk, &tm_wv, bar(BAR_WFULL), ch * CK, 0);
@@ -175,16 +175,20 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                         tma_load_2d(base + p.off_h + nt * p.h_tile + dx * (kNT * HROW), &tm_wh, bar(BAR_WFULL), 0,
                                     dx * p.N + nt * kNT);
             }
+            __syncwarp();
             int xs = 0; uint32_t xph = 0;   // x ring stage / phase
             int hs = 0; uint32_t hph = 0;   // Wh ring stage / phase
             auto load_x = [&](int it) {
                 TileCoord t = decode_tile(first + it * step, p);
                 for (int ch = 0; ch < p.nch; ++ch) {
                     mbar_wait(bar(BAR_XEMPTY + xs), xph ^ 1u);
-                    mbar_arrive_expect_tx(bar(BAR_XFULL + xs), x_bytes + (p.resident ? 0u : v_bytes));
-                    tma_load_4d(base + p.off_x + xs * p.x_stage, &tm_x, bar(BAR_XFULL + xs), ch * CK, t.w0 - 1, t.h0 - 1, t.b);
-                    if (!p.resident)
-                        tma_load_2d(base + p.off_v + xs * p.v_chunk, &tm_wv, bar(BAR_XFULL + xs), ch * CK, 0);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(bar(BAR_XFULL + xs), x_bytes + (p.resident ? 0u : v_bytes));
+                        tma_load_4d(base + p.off_x + xs * p.x_stage, &tm_x, bar(BAR_XFULL + xs), ch * CK, t.w0 - 1, t.h0 - 1, t.b);
+                        if (!p.resident)
+                            tma_load_2d(base + p.off_v + xs * p.v_chunk, &tm_wv, bar(BAR_XFULL + xs), ch * CK, 0);
+                    }
+                    __syncwarp();
                     if (++xs == p.stages) { xs = 0; xph ^= 1u; }
                 }
             };
@@ -192,10 +196,13 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 if (p.resident) return;
                 for (int nt = 0; nt < p.nnt; ++nt) {
                     mbar_wait(bar(BAR_HEMPTY + hs), hph ^ 1u);
-                    mbar_arrive_expect_tx(bar(BAR_HFULL + hs), h_bytes);
-                    for (int dx = 0; dx < 3; ++dx)
-                        tma_load_2d(base + p.off_h + hs * p.h_tile + dx * (kNT * HROW), &tm_wh, bar(BAR_HFULL + hs), 0,
-                                    dx * p.N + nt * kNT);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(bar(BAR_HFULL + hs), h_bytes);
+                        for (int dx = 0; dx < 3; ++dx)
+                            tma_load_2d(base + p.off_h + hs * p.h_tile + dx * (kNT * HROW), &tm_wh, bar(BAR_HFULL + hs), 0,
+                                        dx * p.N + nt * kNT);
+                    }
+                    __syncwarp();
                     if (++hs == 2) { hs = 0; hph ^= 1u; }
                 }
             };
@@ -208,7 +215,7 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         }
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
-        if (lane == 0 && my_tiles > 0) {
+        if (my_tiles > 0) {
             constexpr uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KP >> 3) << 17) | (8u << 24);
             constexpr uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kNT >> 3) << 17) | (8u << 24);
             constexpr uint64_t xdesc = desc_hi(16, 8 * XROW, swz_type(XROW));     // x tile and Wv chunk (swizzled, K-major)
@@ -227,16 +234,19 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                     tc_fence_after_sync();
                     const uint64_t a0 = xdesc + ((base + p.off_x + xs * p.x_stage) >> 4);
                     const uint64_t b0 = xdesc + ((base + p.off_v + (p.resident ? ch : xs) * p.v_chunk) >> 4);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int dy = 0; dy < 3; ++dy)
+                        for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-                        for (int kk = 0; kk < CK / 16; ++kk)
-                            umma_bf16(d, a0 + ((dy * kTileCols * XROW + kk * 32) >> 4), b0 + ((dy * KP * XROW + kk * 32) >> 4),
-                                      idesc1, (uint32_t)((ch | dy | kk) != 0));
-                    umma_commit(bar(BAR_XEMPTY + xs));
+                            for (int kk = 0; kk < CK / 16; ++kk)
+                                umma_bf16(d, a0 + ((dy * kTileCols * XROW + kk * 32) >> 4), b0 + ((dy * KP * XROW + kk * 32) >> 4),
+                                          idesc1, (uint32_t)((ch | dy | kk) != 0));
+                        umma_commit(bar(BAR_XEMPTY + xs));
+                        if (ch == p.nch - 1) umma_commit(bar(BAR_TACC_FULL + buf));
+                    }
+                    __syncwarp();
                     if (++xs == p.stages) { xs = 0; xph ^= 1u; }
                 }
-                umma_commit(bar(BAR_TACC_FULL + buf));
             };
             auto gemm2 = [&](int j) {
                 const int buf = j & 1;
@@ -257,16 +267,19 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                     tc_fence_after_sync();
                     const uint64_t b0 = hdesc + (hb >> 4);
                     const uint32_t d = tmem_Y + yb * 64;
+                    if (elect_one()) {
 #pragma unroll
-                    for (int dx = 0; dx < 3; ++dx)
+                        for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
-                        for (int kk = 0; kk < KP / 16; ++kk)
-                            umma_bf16(d, a0 + ((dx * kTSbo + kk * 2 * kTLbo) >> 4), b0 + ((dx * (kNT * HROW) + kk * 32) >> 4),
-                                      idesc2, (uint32_t)((dx | kk) != 0));
-                    if (!p.resident) umma_commit(bar(BAR_HEMPTY + yb));
-                    umma_commit(bar(BAR_YACC_FULL + yb));
+                            for (int kk = 0; kk < KP / 16; ++kk)
+                                umma_bf16(d, a0 + ((dx * kTSbo + kk * 2 * kTLbo) >> 4), b0 + ((dx * (kNT * HROW) + kk * 32) >> 4),
+                                          idesc2, (uint32_t)((dx | kk) != 0));
+                        if (!p.resident) umma_commit(bar(BAR_HEMPTY + yb));
+                        umma_commit(bar(BAR_YACC_FULL + yb));
+                        if (nt == p.nnt - 1) umma_commit(bar(BAR_TSM_EMPTY + buf));
+                    }
+                    __syncwarp();
                 }
-                umma_commit(bar(BAR_TSM_EMPTY + buf));
             };
             gemm1(0);
             for (int it = 0; it < my_tiles; ++it) {

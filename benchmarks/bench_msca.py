@@ -1,0 +1,127 @@
+#!/usr/bin/env python
+"""BASELINE config 4: MSCA block (SegNeXt MSCAN-T shapes at 512x512 input, batch 32), un-reparameterised vs
+re-parameterised forward, on one B200.
+
+Times each of the four MSCAN-T stage shapes (C,H) = (32,128) (64,64) (160,32) (256,16) for
+  original            MSCA with 3 strip cascades + identity
+  rep d0+fix          single 21x21 depthwise kernel + border fix  (MscaRep(decomp=0, fix=True))
+  rep d1+fix          one 1x21 . 21x1 cascade + border fix        (MscaRep(decomp=1, fix=True))
+through this backend (bf16 and fp32), and — with --torch — through stock torch modules on the same GPU
+(cuDNN, channels_last bf16): the library path the kernels have to beat.  Prints one JSON object per line.
+
+    python benchmarks/bench_msca.py [--batch 32] [--iters 20] [--dtype bf16|f32] [--torch] [--cpu]
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for _p in (ROOT, os.path.join(ROOT, "convnet-approximater_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+SHAPES = [(32, 128, 3), (64, 64, 3), (160, 32, 5), (256, 16, 2)]   # (C, H=W, number of blocks in MSCAN-T)
+
+
+def time_cuda(fn, iters, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def torch_msca(C):
+    """Stock-torch restatement of the reference module (layers/msca.py, depth_seperable_conv.py) for the GPU library baseline."""
+    from torch import nn
+
+    class Cascade(nn.Module):
+        def __init__(s, k):
+            super().__init__()
+            s.c1 = nn.Conv2d(C, C, (1, k), padding=(0, k // 2), groups=C)
+            s.c2 = nn.Conv2d(C, C, (k, 1), padding=(k // 2, 0), groups=C)
+
+        def forward(s, x):
+            return s.c2(s.c1(x))
+
+    class M(nn.Module):
+        def __init__(s):
+            super().__init__()
+            s.conv0 = nn.Conv2d(C, C, 5, padding=2, groups=C)
+            s.br = nn.ModuleList([Cascade(k) for k in (7, 11, 21)])
+            s.mix = nn.Conv2d(C, C, 1)
+
+        def forward(s, x):
+            a = s.conv0(x)
+            return x * s.mix(sum([b(a) for b in s.br] + [a]))
+    return M()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--torch", action="store_true", help="also time stock torch/cuDNN on the GPU")
+    args = ap.parse_args()
+    from approx import backend as B
+    from approx.layers import MSCA
+    from approx.core import MscaRep
+
+    dt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    esz = 2 if dt == torch.bfloat16 else 4
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    total = {}
+    for (C, H, nblk) in SHAPES:
+        torch.manual_seed(42)
+        src = MSCA(C, 5, (7, 11, 21))
+        variants = {"original": src}
+        for name, (d, f) in {"rep_d0_fix": (0, True), "rep_d1_fix": (1, True)}.items():
+            app = MscaRep(decomp=d, fix=f)
+            sub = app.initialize(src)
+            import io, contextlib
+            with contextlib.redirect_stdout(io.StringIO()):
+                app.optimize(sub)
+            variants[name] = app.postprocess(sub)
+        x = torch.randn(args.batch, H, H, C, device="cuda").to(dt)          # NHWC resident in HBM
+        elems = args.batch * H * H * C
+        for name, m in variants.items():
+            m = m.cuda().to(dt).eval()
+            with torch.no_grad():
+                n0 = B.launch_count()
+                m.forward_nhwc(x)
+                launches = B.launch_count() - n0
+                ms = time_cuda(lambda: m.forward_nhwc(x), args.iters)
+            rec = {"bench": "msca_block", "variant": name, "dtype": args.dtype, "C": C, "H": H, "batch": args.batch,
+                   "ms": ms, "launches": launches, "images_per_s": args.batch / ms * 1e3,
+                   "min_traffic_GBps": 2 * elems * esz / ms / 1e6, "frac_hbm_min_traffic": 2 * elems * esz / ms / 1e6 / hbm}
+            print(json.dumps(rec))
+            total[name] = total.get(name, 0.0) + ms * nblk
+        if args.torch:
+            tm = torch_msca(C).cuda().to(dt).to(memory_format=torch.channels_last).eval()
+            xt = x.permute(0, 3, 1, 2)
+            with torch.no_grad():
+                ms = time_cuda(lambda: tm(xt), args.iters)
+            print(json.dumps({"bench": "msca_block", "variant": "torch_cudnn_original", "dtype": args.dtype, "C": C, "H": H,
+                              "batch": args.batch, "ms": ms, "images_per_s": args.batch / ms * 1e3}))
+            total["torch_cudnn_original"] = total.get("torch_cudnn_original", 0.0) + ms * nblk
+    for name, ms in total.items():
+        print(json.dumps({"bench": "mscan_t_all_13_msca_blocks", "variant": name, "dtype": args.dtype, "batch": args.batch,
+                          "ms": ms, "images_per_s": args.batch / ms * 1e3}))
+
+
+if __name__ == "__main__":
+    main()

@@ -33,6 +33,8 @@ _SIGS = {
     "cna_lowrank2_fused_forward": "pppppiiiiiiiip",
     "cna_lowrank2_fused_supported": "iiiiii",
     "cna_maxpool2x2": "ppiiiiip",
+    "cna_msca_sd_supported": "iiipi",
+    "cna_msca_sd_forward": "pppppppppipiiiiiiip",
     "cna_svd_small_batched": "ppppiiip",
     "cna_lowrank1_svd_fit": "piiippp",
     "cna_msca_equiv_kernel": "pppppiipppp",
@@ -250,6 +252,26 @@ def maxpool2x2(x):
     y = torch.empty((B, H // 2, W // 2, C), device=x.device, dtype=x.dtype)
     with torch.cuda.device(x.device):
         _check(lib().cna_maxpool2x2(_p(x), _p(y), B, H, W, C, dtype_code(x.dtype), _stream(x)))
+    return y
+
+
+def msca_sd_supported(C, k1, ks, dtype):
+    arr = (c_int * len(ks))(*ks)
+    return bool(lib().cna_msca_sd_supported(C, k1, len(ks), ctypes.cast(arr, c_void_p), dtype_code(dtype)))
+
+
+def msca_sd(x, w0, b0, w1cat, b1cat, w2cat, b2cat, ks, identity, res=None):
+    """Fused conv0 -> strip cascades (+identity, +FixPaddingBias) on NHWC x; weights fp32 tap-major ([taps][C])."""
+    _ready(x)
+    B, H, W, C = x.shape
+    assert x.is_contiguous()
+    y = torch.empty_like(x)
+    arr = (c_int * len(ks))(*ks)
+    res_p = 0 if res is None else res.shape[2]
+    with torch.cuda.device(x.device):
+        _check(lib().cna_msca_sd_forward(_p(x), _p(y), _p(w0), _p(b0), _p(w1cat), _p(b1cat), _p(w2cat), _p(b2cat), _p(res),
+                                         res_p, ctypes.cast(arr, c_void_p), len(ks), int(identity), B, H, W, C,
+                                         dtype_code(x.dtype), _stream(x)))
     return y
 
 

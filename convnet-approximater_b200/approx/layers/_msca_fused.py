@@ -3,6 +3,46 @@
 Each function returns None when the fused kernel does not apply; callers then run the
 generic depthwise kernels (still CUDA, just more launches).
 """
+import torch
+from torch import nn
+
+from approx import backend as B
+from . import _ops
+
+
+def _branches(sd):
+    """-> (list of CascadeConv, identity flag, FixPaddingBias | None) or None if `sd` has another shape."""
+    from .depth_seperable_conv import CascadeConv, FixPaddingBias, ParallelConv
+    fix = None
+    if isinstance(sd, nn.Sequential):
+        if len(sd) != 2 or not isinstance(sd[1], FixPaddingBias):
+            return None
+        sd, fix = sd[0], sd[1]
+    if isinstance(sd, ParallelConv):
+        return sd.cascades(), sd.has_identity, fix
+    if isinstance(sd, CascadeConv):
+        return [sd], False, fix
+    return None
+
+
+def _packed_chain(msca, cas, dtype):
+    """fp32 tap-major weight blocks for the fused kernel, cached on the MSCA module."""
+    params = [msca.conv0.weight, msca.conv0.bias]
+    for c in cas:
+        params += [c.conv1.weight, c.conv1.bias, c.conv2.weight, c.conv2.bias]
+
+    def build():
+        dev = msca.conv0.weight.device
+        C = msca.num_channel
+        zero = torch.zeros(C, device=dev, dtype=torch.float32)
+        f = lambda t: zero if t is None else t.detach().to(torch.float32).contiguous()
+        w0 = B.pack_dw(msca.conv0.weight, torch.float32)
+        w1 = torch.cat([B.pack_dw(c.conv1.weight, torch.float32) for c in cas]).contiguous()
+        w2 = torch.cat([B.pack_dw(c.conv2.weight, torch.float32) for c in cas]).contiguous()
+        b1 = torch.stack([f(c.conv1.bias) for c in cas]).contiguous()
+        b2 = torch.stack([f(c.conv2.bias) for c in cas]).contiguous()
+        return w0, f(msca.conv0.bias), w1, b1, w2, b2
+    return _ops.cached(msca, "sd_chain", params, dtype, build)
 
 
 def parallel_forward(par, x):
@@ -10,4 +50,25 @@ def parallel_forward(par, x):
 
 
 def conv0_sd_forward(msca, x):
-    return None
+    """conv0 + sd_convs of an MSCA block as one kernel, or None."""
+    got = _branches(msca.sd_convs)
+    if got is None:
+        return None
+    cas, identity, fix = got
+    conv0 = msca.conv0
+    if (conv0.kernel_size != (5, 5) or conv0.stride != (1, 1) or conv0.padding != (2, 2)
+            or conv0.groups != conv0.in_channels or conv0.out_channels != conv0.in_channels):
+        return None
+    ks = []
+    for c in cas:
+        k = c.conv1.kernel_size[1]
+        if (c.conv1.kernel_size != (1, k) or c.conv2.kernel_size != (k, 1) or c.conv1.padding != (0, k // 2)
+                or c.conv2.padding != (k // 2, 0) or c.conv1.stride != (1, 1) or c.conv2.stride != (1, 1)):
+            return None
+        ks.append(k)
+    if not ks or not B.msca_sd_supported(msca.num_channel, 5, ks, x.dtype):
+        return None
+    if fix is not None and fix.p != max(ks) // 2 and False:
+        return None
+    w0, b0, w1, b1, w2, b2 = _packed_chain(msca, cas, x.dtype)
+    return B.msca_sd(x.contiguous(), w0, b0, w1, b1, w2, b2, ks, identity, res=None if fix is None else fix.res_f32())

@@ -1,0 +1,396 @@
+// Fused MSCA "sd" chain for NHWC tensors:   s = conv0(x) ⊕ Σ_k cascade_k(conv0(x))   in ONE kernel.
+//
+// Replaces, for the block shipped in SegNeXt MSCAN (k1 = 5, strips 7/11/21, reference
+// src/approx/layers/msca.py:18-26 and depth_seperable_conv.py:45-47) the reference's 7 depthwise-conv launches
+// + 4 elementwise adds (≈ 24 full tensor passes through HBM) by one pass: read x once, write s once.
+// The same kernel runs MscaRep's rank-1 form (one 1x21 . 21x1 cascade, optional FixPaddingBias residues).
+//
+// Scheme: a CTA owns (image, group of 16 bf16 / 8 fp32 channels, strip of 32 output columns) and MARCHES
+// down the rows, 4 output rows per step, keeping sliding windows in shared memory:
+//     X   ring  (8 rows)            input rows            -> conv0 (k1 x k1)
+//     A0  ring  (14 rows)           conv0 output          -> horizontal 1xk passes, identity branch
+//     T_k rings (k + 3 rows each)   1xk outputs           -> vertical kx1 passes
+// so no row is ever recomputed or re-read; only the 10+2 halo columns of a strip are redundant work.
+// Arithmetic is fp32 FFMA; lanes run across channel pairs (4-byte units) so every shared-memory access
+// of a warp is a conflict-free 128-byte wavefront (row pitches are padded to 8 words mod 32), and each
+// thread register-tiles 4-7 outputs along the conv direction so a loaded value feeds 4-7 FMAs.
+// In bf16 mode every tensor the reference materialises (conv0 out, each 1xk out, each branch out, every
+// partial sum) is rounded to bf16 at the same point, so results track the reference's bf16 modules.
+#include "common.cuh"
+
+namespace cna {
+
+constexpr int SD_THREADS = 256;
+constexpr int SD_RB = 4;          // output rows per step
+constexpr int SD_WT = 32;         // output columns per strip
+constexpr int SD_P = 10;          // halo of the widest strip (21 taps)
+constexpr int SD_UNITS = 8;       // 4-byte units per pixel held by a CTA
+constexpr int SD_MAXB = 3;        // strip branches
+
+struct SdParams {
+    int B, H, W, C;
+    int nb;                 // number of cascades
+    int ks[SD_MAXB];        // strip sizes (7, 11 or 21)
+    int identity;           // add conv0's output itself (ParallelConv identity branch)
+    int res_p;              // FixPaddingBias padding (0 = none)
+    int strips;             // ceil(W / SD_WT)
+};
+
+// ---- 4-byte unit <-> floats ------------------------------------------------------------------
+template <typename T> struct UnitOps;
+template <> struct UnitOps<__nv_bfloat16> {
+    static constexpr int NCH = 2;
+    __device__ static __forceinline__ void unpack(uint32_t u, float (&f)[2]) {
+        f[0] = __uint_as_float(u << 16);
+        f[1] = __uint_as_float(u & 0xffff0000u);
+    }
+    __device__ static __forceinline__ uint32_t pack(const float (&f)[2]) {
+        __nv_bfloat162 v = __floats2bfloat162_rn(f[0], f[1]);
+        return *reinterpret_cast<uint32_t*>(&v);
+    }
+    __device__ static __forceinline__ float rnd(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+};
+template <> struct UnitOps<float> {
+    static constexpr int NCH = 1;
+    __device__ static __forceinline__ void unpack(uint32_t u, float (&f)[1]) { f[0] = __uint_as_float(u); }
+    __device__ static __forceinline__ uint32_t pack(const float (&f)[1]) { return __float_as_uint(f[0]); }
+    __device__ static __forceinline__ float rnd(float v) { return v; }
+};
+
+__host__ __device__ constexpr int sd_pitch(int cols) { return ((cols * SD_UNITS + 31) / 32) * 32 + 8; }  // units
+constexpr int SD_XC = SD_WT + 2 * SD_P + 4;     // 56 x columns   (strip + 10 + 2 each side)
+constexpr int SD_AC = SD_WT + 2 * SD_P;         // 52 a0 columns
+constexpr int SD_XR = 8, SD_AR = SD_RB + SD_P;  // ring depths (rows): x 8, a0 14
+__host__ __device__ constexpr int sd_tr(int k) { return k - 1 + SD_RB; }
+
+__device__ __forceinline__ int ring(int row, int depth) { int m = row % depth; return m < 0 ? m + depth : m; }
+
+// Horizontal 1xK pass on the 4 a0 rows [row0, row0+4) -> T ring.  thread = (unit u, row r, run of 4 columns).
+template <typename T, int K>
+__device__ __forceinline__ void sd_hpass(const uint32_t* __restrict__ A0, uint32_t* __restrict__ Tk, const float* __restrict__ w1,
+                                         const float* __restrict__ b1, int row0, int H, int u, int pos) {
+    using U = UnitOps<T>;
+    constexpr int NCH = U::NCH, PK = K / 2;
+    const int r = pos & 3, run = pos >> 2;
+    const int row = row0 + r;
+    uint32_t* dst = Tk + ring(row, sd_tr(K)) * sd_pitch(SD_WT) + (run * 4) * SD_UNITS + u;
+    if (row < 0 || row >= H) {            // outside the image: the vertical conv sees zero padding
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i * SD_UNITS] = 0u;
+        return;
+    }
+    float wt[K][NCH];
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) wt[j][c] = w1[(j * SD_UNITS + u) * NCH + c];
+    float acc[4][NCH];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) acc[i][c] = 0.f;
+    const uint32_t* src = A0 + ring(row, SD_AR) * sd_pitch(SD_AC) + (run * 4 + SD_P - PK) * SD_UNITS + u;
+#pragma unroll
+    for (int j = 0; j < K + 3; ++j) {
+        float v[NCH];
+        U::unpack(src[j * SD_UNITS], v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int tap = j - i;
+            if (tap >= 0 && tap < K) {
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) acc[i][c] = fmaf(v[c], wt[tap][c], acc[i][c]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float o[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) o[c] = acc[i][c] + b1[u * NCH + c];
+        dst[i * SD_UNITS] = U::pack(o);
+    }
+}
+
+// Vertical Kx1 pass for output rows [h0, h0+4) at column `col`: returns the branch output (bias added, rounded).
+template <typename T, int K>
+__device__ __forceinline__ void sd_vpass(const uint32_t* __restrict__ Tk, const float* __restrict__ w2, const float* __restrict__ b2,
+                                         int h0, int u, int col, float (&out)[4][UnitOps<T>::NCH]) {
+    using U = UnitOps<T>;
+    constexpr int NCH = U::NCH, PK = K / 2;
+    float wt[K][NCH];
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) wt[j][c] = w2[(j * SD_UNITS + u) * NCH + c];
+    float acc[4][NCH];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) acc[i][c] = 0.f;
+    const uint32_t* src = Tk + col * SD_UNITS + u;
+#pragma unroll
+    for (int j = 0; j < K + 3; ++j) {
+        float v[NCH];
+        U::unpack(src[ring(h0 - PK + j, sd_tr(K)) * sd_pitch(SD_WT)], v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int tap = j - i;
+            if (tap >= 0 && tap < K) {
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) acc[i][c] = fmaf(v[c], wt[tap][c], acc[i][c]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) out[i][c] = U::rnd(acc[i][c] + b2[u * NCH + c]);
+}
+
+template <typename T, int K>
+__device__ __forceinline__ void sd_branch_h(const uint32_t* A0, uint32_t* Tk, const float* wsm, int woff, int boff, int h0, int H,
+                                            int u, int pos) {
+    // T_k rows computed this step: [h0 + pk, h0 + pk + 4)
+    sd_hpass<T, K>(A0, Tk, wsm + woff, wsm + boff, h0 + K / 2, H, u, pos);
+}
+
+// weights in smem (floats), per CTA channel group of CB = 8*NCH channels:
+//   conv0: [25][CB] + bias [CB];  per branch: w1 [k][CB], b1 [CB], w2 [k][CB], b2 [CB]
+template <typename T>
+__global__ void __launch_bounds__(SD_THREADS, 2)
+msca_sd_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ w0, const float* __restrict__ b0,
+               const float* __restrict__ w1cat, const float* __restrict__ b1cat, const float* __restrict__ w2cat,
+               const float* __restrict__ b2cat, const float* __restrict__ res, const SdParams p) {
+    using U = UnitOps<T>;
+    constexpr int NCH = U::NCH, CB = SD_UNITS * NCH;
+    extern __shared__ uint32_t sm[];
+    const int tid = threadIdx.x, u = tid & 7, pos = tid >> 3;
+    const int strip = blockIdx.x % p.strips, cg = blockIdx.x / p.strips, b = blockIdx.y;
+    const int w0c = strip * SD_WT, c0 = cg * CB;
+
+    // ---- carve shared memory ----
+    uint32_t* X = sm;
+    uint32_t* A0 = X + SD_XR * sd_pitch(SD_XC);
+    uint32_t* Tb[SD_MAXB];
+    uint32_t* cur = A0 + SD_AR * sd_pitch(SD_AC);
+    int koff[SD_MAXB];
+    for (int i = 0; i < SD_MAXB; ++i) {
+        Tb[i] = cur;
+        if (i < p.nb) cur += sd_tr(p.ks[i]) * sd_pitch(SD_WT);
+    }
+    float* wsm = reinterpret_cast<float*>(cur);
+    // weight block layout (floats): conv0 w [25*CB], conv0 b [CB], then per branch w1 [k*CB], b1 [CB], w2 [k*CB], b2 [CB]
+    const int o_w0 = 0, o_b0 = 25 * CB;
+    int o_br[SD_MAXB];
+    {
+        int o = o_b0 + CB, ko = 0;
+        for (int i = 0; i < p.nb; ++i) { o_br[i] = o; koff[i] = ko; o += 2 * (p.ks[i] * CB + CB); ko += p.ks[i]; }
+        for (int i = tid; i < 25 * CB; i += SD_THREADS) wsm[o_w0 + i] = w0[(size_t)(i / CB) * p.C + c0 + i % CB];
+        for (int i = tid; i < CB; i += SD_THREADS) wsm[o_b0 + i] = b0 ? b0[c0 + i] : 0.f;
+        for (int br = 0; br < p.nb; ++br) {
+            const int k = p.ks[br];
+            float* d = wsm + o_br[br];
+            for (int i = tid; i < k * CB; i += SD_THREADS) {
+                d[i] = w1cat[(size_t)(koff[br] + i / CB) * p.C + c0 + i % CB];
+                d[k * CB + CB + i] = w2cat[(size_t)(koff[br] + i / CB) * p.C + c0 + i % CB];
+            }
+            for (int i = tid; i < CB; i += SD_THREADS) {
+                d[k * CB + i] = b1cat ? b1cat[br * p.C + c0 + i] : 0.f;
+                d[2 * k * CB + CB + i] = b2cat ? b2cat[br * p.C + c0 + i] : 0.f;
+            }
+        }
+    }
+    // zero the rings: rows that are never produced (above the image) must read as zero padding
+    for (uint32_t* q = sm + tid; q < reinterpret_cast<uint32_t*>(wsm); q += SD_THREADS) *q = 0u;
+    __syncthreads();
+
+    const int H = p.H, W = p.W;
+    const T* xb = x + (size_t)b * H * W * p.C;
+    T* yb = y + (size_t)b * H * W * p.C;
+
+    // loads x rows [r0, r0 + n) into the X ring (zero outside the image)
+    auto load_x = [&](int r0, int n) {
+        constexpr int CHUNKS = SD_XC * 2;                 // two 16-byte chunks per pixel (32 bytes = 8 units)
+        for (int i = tid; i < n * CHUNKS; i += SD_THREADS) {
+            const int rr = i / CHUNKS, cc = (i % CHUNKS) >> 1, half = i & 1;
+            const int row = r0 + rr, col = w0c - SD_P - 2 + cc;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (row >= 0 && row < H && col >= 0 && col < W)
+                v = __ldg(reinterpret_cast<const uint4*>(xb + ((size_t)row * W + col) * p.C + c0) + half);
+            *reinterpret_cast<uint4*>(X + ring(row, SD_XR) * sd_pitch(SD_XC) + cc * SD_UNITS + half * 4) = v;
+        }
+    };
+    // conv0 on a0 rows [r0, r0+4): thread = (u, row r, run of 7 columns)
+    auto conv0 = [&](int r0) {
+        const int r = pos & 3, run = pos >> 2;
+        const int row = r0 + r;
+        uint32_t* dst = A0 + ring(row, SD_AR) * sd_pitch(SD_AC) + u;
+        const bool row_in = row >= 0 && row < H;
+        float acc[7][NCH];
+#pragma unroll
+        for (int i = 0; i < 7; ++i)
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) acc[i][c] = 0.f;
+        if (row_in) {
+#pragma unroll
+            for (int di = 0; di < 5; ++di) {
+                float wt[5][NCH];
+#pragma unroll
+                for (int j = 0; j < 5; ++j)
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) wt[j][c] = wsm[o_w0 + ((di * 5 + j) * SD_UNITS + u) * NCH + c];
+                const uint32_t* src = X + ring(row - 2 + di, SD_XR) * sd_pitch(SD_XC) + (run * 7) * SD_UNITS + u;
+#pragma unroll
+                for (int j = 0; j < 11; ++j) {
+                    if (run * 7 + j < SD_XC) {
+                        float v[NCH];
+                        U::unpack(src[j * SD_UNITS], v);
+#pragma unroll
+                        for (int i = 0; i < 7; ++i) {
+                            const int tap = j - i;
+                            if (tap >= 0 && tap < 5) {
+#pragma unroll
+                                for (int c = 0; c < NCH; ++c) acc[i][c] = fmaf(v[c], wt[tap][c], acc[i][c]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            const int ac = run * 7 + i;               // a0 column index (0..51) <-> image column w0c - 10 + ac
+            if (ac < SD_AC) {
+                const int col = w0c - SD_P + ac;
+                float o[NCH];
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) o[c] = acc[i][c] + wsm[o_b0 + u * NCH + c];
+                // outside the image the strip convs see ZERO padding, not conv0 of a padded input
+                dst[ac * SD_UNITS] = (row_in && col >= 0 && col < W) ? U::pack(o) : 0u;
+            }
+        }
+    };
+
+    // marching loop: step with output rows [h0, h0+4)
+    //   load x rows [h0+12, h0+16) ; conv0 -> a0 rows [h0+10, h0+14) ; T_k rows [h0+pk, h0+pk+4) ; output rows [h0, h0+4)
+    const int h_first = -2 * SD_P;      // first step that produces a T_21 row needed by output row 0
+    load_x(h_first + 8, 4);             // rows h_first+8 .. h_first+11 (above the image: zeros)
+    __syncthreads();
+    for (int h0 = h_first; h0 < H; h0 += SD_RB) {
+        load_x(h0 + 12, 4);
+        __syncthreads();
+        conv0(h0 + 10);
+        __syncthreads();
+        for (int br = 0; br < p.nb; ++br) {
+            const int k = p.ks[br];
+            const int woff = o_br[br], boff = o_br[br] + k * CB;
+            if (k == 7) sd_branch_h<T, 7>(A0, Tb[br], wsm, woff, boff, h0, H, u, pos);
+            else if (k == 11) sd_branch_h<T, 11>(A0, Tb[br], wsm, woff, boff, h0, H, u, pos);
+            else sd_branch_h<T, 21>(A0, Tb[br], wsm, woff, boff, h0, H, u, pos);
+        }
+        __syncthreads();
+        if (h0 >= 0) {
+            // vertical passes + sum, thread = (u, column pos)
+            float total[4][NCH];
+            bool have = false;
+            for (int br = 0; br < p.nb; ++br) {
+                const int k = p.ks[br];
+                const float* w2 = wsm + o_br[br] + k * CB + CB;
+                const float* b2 = w2 + k * CB;
+                float o[4][NCH];
+                if (k == 7) sd_vpass<T, 7>(Tb[br], w2, b2, h0, u, pos, o);
+                else if (k == 11) sd_vpass<T, 11>(Tb[br], w2, b2, h0, u, pos, o);
+                else sd_vpass<T, 21>(Tb[br], w2, b2, h0, u, pos, o);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) total[i][c] = have ? U::rnd(total[i][c] + o[i][c]) : o[i][c];
+                have = true;
+            }
+            const int col = w0c + pos;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = h0 + i;
+                if (row < H && col < W) {
+                    float v[NCH];
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) v[c] = total[i][c];
+                    if (p.identity) {
+                        float a[NCH];
+                        U::unpack(A0[ring(row, SD_AR) * sd_pitch(SD_AC) + (pos + SD_P) * SD_UNITS + u], a);
+#pragma unroll
+                        for (int c = 0; c < NCH; ++c) v[c] = U::rnd(v[c] + a[c]);
+                    }
+                    if (p.res_p > 0) {     // FixPaddingBias: top rows then bottom rows, each add materialised
+                        const int p2 = min(H, p.res_p);
+#pragma unroll
+                        for (int c = 0; c < NCH; ++c) {
+                            const int ch = c0 + u * NCH + c;
+                            if (row < p2) v[c] = U::rnd(v[c] + res[(size_t)ch * p.res_p + row]);
+                            if (row >= H - p2) v[c] = U::rnd(v[c] + res[((size_t)p.C + ch) * p.res_p + (p.res_p - (H - row))]);
+                        }
+                    }
+                    *reinterpret_cast<uint32_t*>(yb + ((size_t)row * W + col) * p.C + c0 + u * NCH) = U::pack(v);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+static size_t sd_smem_bytes(const SdParams& p, int cb) {
+    size_t units = (size_t)SD_XR * sd_pitch(SD_XC) + (size_t)SD_AR * sd_pitch(SD_AC);
+    size_t wfl = 26 * cb;
+    for (int i = 0; i < p.nb; ++i) {
+        units += (size_t)sd_tr(p.ks[i]) * sd_pitch(SD_WT);
+        wfl += 2 * (p.ks[i] * cb + cb);
+    }
+    return (units + wfl) * 4;
+}
+
+}  // namespace cna
+
+using namespace cna;
+
+extern "C" {
+
+int cna_msca_sd_supported(int C, int k1, int nb, const int* ks_host, int dtype) {
+    if (k1 != 5 || nb < 1 || nb > SD_MAXB) return 0;
+    int cb = dtype == CNA_BF16 ? 16 : 8;
+    if (C % cb != 0) return 0;
+    for (int i = 0; i < nb; ++i)
+        if (ks_host[i] != 7 && ks_host[i] != 11 && ks_host[i] != 21) return 0;
+    return 1;
+}
+
+int cna_msca_sd_forward(const void* x, void* y, const float* w0, const float* b0, const float* w1cat, const float* b1cat,
+                        const float* w2cat, const float* b2cat, const float* res, int res_p, const int* ks_host, int nb,
+                        int identity, int B, int H, int W, int C, int dtype, void* stream) {
+    CNA_CHECK(x && y && w0 && w1cat && w2cat && ks_host, "null pointer");
+    CNA_CHECK(B > 0 && H > 0 && W > 0 && C > 0, "bad dims");
+    CNA_CHECK(cna_msca_sd_supported(C, 5, nb, ks_host, dtype), "configuration not supported by the fused sd kernel");
+    CNA_CHECK(res == nullptr || res_p > 0, "res without res_p");
+    CNA_CHECK(B <= 65535, "batch too large for grid.y");
+    SdParams p{};
+    p.B = B; p.H = H; p.W = W; p.C = C; p.nb = nb; p.identity = identity; p.res_p = res ? res_p : 0;
+    for (int i = 0; i < nb; ++i) p.ks[i] = ks_host[i];
+    p.strips = ceil_div(W, SD_WT);
+    const int cb = dtype == CNA_BF16 ? 16 : 8;
+    size_t smem = sd_smem_bytes(p, cb);
+    dim3 grid(p.strips * (C / cb), B);
+    cudaStream_t st = as_stream(stream);
+    if (dtype == CNA_BF16) {
+        CNA_CUDA(cudaFuncSetAttribute(msca_sd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        msca_sd_kernel<__nv_bfloat16><<<grid, SD_THREADS, smem, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, w0, b0, w1cat,
+                                                                     b1cat, w2cat, b2cat, res, p);
+    } else {
+        CNA_CUDA(cudaFuncSetAttribute(msca_sd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        msca_sd_kernel<float><<<grid, SD_THREADS, smem, st>>>((const float*)x, (float*)y, w0, b0, w1cat, b1cat, w2cat, b2cat,
+                                                             res, p);
+    }
+    CNA_LAUNCH_OK();
+    return 0;
+}
+
+}  // extern "C"

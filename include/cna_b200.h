@@ -101,6 +101,19 @@ int cna_lowrank2_fused_forward(const void* x, const void* wv_packed, const void*
 /* 1 if the fused kernel supports this configuration, else 0 (caller falls back to two cna_conv_taps_forward). */
 int cna_lowrank2_fused_supported(int H, int W, int c_pad, int k_pad, int N, int d);
 
+/* ---- MSCA fused depthwise chain ------------------------------------------------------------------ */
+/* s = [conv0(x)] + sum_b cascade_b(conv0(x))   (conv0: depthwise 5x5 + bias; cascade: depthwise 1xk + b1 then kx1 + b2,
+ * k in {7,11,21}, up to 3 branches; `identity` adds conv0's output; res/res_p = fused FixPaddingBias) in ONE kernel
+ * that reads x once and writes s once (sliding-window rings in shared memory).
+ * w0 [25][C], b0 [C]; w1cat / w2cat [sum k][C]; b1cat / b2cat [nb][C] (NULL = no bias); all fp32.
+ * Needs C % 16 == 0 (bf16) or C % 8 == 0 (fp32).
+ * Replaces MSCA.forward's `sd_convs(conv0(x))` (src/approx/layers/msca.py:26, depth_seperable_conv.py:12-16,45-47) and
+ * MscaRep's decomp>=1 forms (src/approx/core/msca_rep.py:46-55). */
+int cna_msca_sd_supported(int C, int k1, int nb, const int* ks_host, int dtype);
+int cna_msca_sd_forward(const void* x, void* y, const float* w0, const float* b0, const float* w1cat, const float* b1cat,
+                        const float* w2cat, const float* b2cat, const float* res, int res_p, const int* ks_host, int nb,
+                        int identity, int B, int H, int W, int C, int dtype, void* stream);
+
 /* ---- fitting step (device-side small linear algebra) ------------------------------------------- */
 /* Batched SVD of small matrices, A (batch,m,n) fp32 row-major with 1 <= n <= m <= 64:
  * U (batch,m,n), S (batch,n) descending, Vh (batch,n,n).  One-sided Jacobi in fp64, one warp per matrix.

@@ -163,3 +163,64 @@ def test_bf16_msca_against_bf16_oracle(golden):
                          sd["channel_mix.weight"], sd["channel_mix.bias"])
     y = mb.cuda()(x.cuda())
     assert O.compare4d(ref.float(), y.float().cpu()) < 3e-3
+
+
+def _oracle_msca(m, x, dt):
+    """Oracle forward of an (original) MSCA module `m` in dtype dt on CPU."""
+    sd = {k: v.detach().cpu().to(dt) for k, v in m.state_dict().items()}
+    br = [tuple(sd[f"sd_convs.branches.{i}.{n}"] for n in ("conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias"))
+          for i in range(3)]
+    return O.msca_forward(x.to(dt), sd["conv0.weight"], sd["conv0.bias"], lambda a: O.parallel_forward(a, br, True),
+                          sd["channel_mix.weight"], sd["channel_mix.bias"])
+
+
+@pytest.mark.parametrize("C,H,W", [(32, 40, 50), (16, 7, 9), (64, 33, 32), (48, 21, 70)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_msca_fused_sd_kernel_vs_oracle(C, H, W, dt):
+    """The fused marching kernel (conv0 -> 3 strip cascades + identity) on ragged sizes, fp32 and bf16."""
+    from approx import backend as B
+    from approx.layers import MSCA
+    torch.manual_seed(C + H)
+    m = MSCA(C, 5, (7, 11, 21))
+    x = torch.randn(2, C, H, W)
+    ref = _oracle_msca(m, x, dt)
+    md = m.cuda().to(dt)
+    n0 = B.launch_count()
+    y = md(x.cuda().to(dt))
+    assert B.launch_count() - n0 <= 12      # packing + layout + 2 compute kernels (fused sd, mix+gate)
+    assert O.compare4d(ref.float(), y.float().cpu()) < (TOL if dt == torch.float32 else 3e-3)
+    n0 = B.launch_count()
+    md(x.cuda().to(dt))
+    assert B.launch_count() - n0 <= 3       # cached weights: layout + fused sd + mix/gate
+
+
+@pytest.mark.parametrize("decomp,fix", [(1, True), (2, True), (3, False), (0, True)])
+def test_msca_rep_fused_matches_unfused(decomp, fix):
+    """Re-parameterised forms through the fused kernel agree with the reference algebra on a 32-channel block."""
+    from approx.core import MscaRep
+    from approx.layers import MSCA
+    torch.manual_seed(5)
+    src = MSCA(32, 5, (7, 11, 21))
+    x = torch.randn(2, 32, 26, 45)
+    app = MscaRep(decomp=decomp, fix=fix)
+    sub = app.initialize(src)
+    with contextlib.redirect_stdout(io.StringIO()):
+        app.optimize(sub)
+    tgt = app.postprocess(sub)
+    # oracle: same re-parameterisation applied with the CPU oracle functions
+    sd = {k: v.detach().cpu() for k, v in src.state_dict().items()}
+    br = [tuple(sd[f"sd_convs.branches.{i}.{n}"] for n in ("conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias"))
+          for i in range(3)]
+    w, b, r = O.msca_equivalent_kernel(br, 32)
+    import torch.nn.functional as F
+    if decomp == 0:
+        sdf = lambda a: O.fix_padding_bias(F.conv2d(a, w, b, padding=10, groups=32), r, 10)
+    else:
+        fac, _ = O.msca_rep_factors(w, decomp)
+        def sdf(a):
+            brs = [(c1, None, c2, b if j == decomp - 1 else None) for j, (c1, c2) in enumerate(fac)]
+            yy = O.parallel_forward(a, brs, False)
+            return O.fix_padding_bias(yy, r, 10) if fix else yy
+    ref = O.msca_forward(x, sd["conv0.weight"], sd["conv0.bias"], sdf, sd["channel_mix.weight"], sd["channel_mix.bias"])
+    y = tgt.cuda()(x.cuda())
+    assert O.compare4d(ref, y.cpu()) < 5e-5

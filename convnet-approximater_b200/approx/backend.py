@@ -36,6 +36,11 @@ _SIGS = {
     "cna_msca_sd_supported": "iiipi",
     "cna_msca_sd_forward": "pppppppppipiiiiiiip",
     "cna_svd_small_batched": "ppppiiip",
+    "cna_svd_jacobi_large": "piiipppip",
+    "cna_l2_recon_loss_grad": "pppppiLfip",
+    "cna_conv_taps_wgrad": "ppppiiiiiiiiip",
+    "cna_pack_taps_weight_dgrad": "ppiiiip",
+    "cna_adamw_step": "ppppLfffffifp",
     "cna_lowrank1_svd_fit": "piiippp",
     "cna_msca_equiv_kernel": "pppppiipppp",
 }
@@ -53,7 +58,7 @@ def lib():
         for name, sig in _SIGS.items():
             fn = getattr(L, name)
             fn.restype = c_int
-            fn.argtypes = [{"p": c_void_p, "i": c_int, "L": ctypes.c_longlong}[ch] for ch in sig]
+            fn.argtypes = [{"p": c_void_p, "i": c_int, "L": ctypes.c_longlong, "f": ctypes.c_float}[ch] for ch in sig]
         L.cna_last_error.restype = ctypes.c_char_p
         L.cna_launch_count.restype = ctypes.c_ulonglong
         L.cna_version.restype = c_int
@@ -374,3 +379,77 @@ def msca_equiv_kernel(w1s, b1s, w2s, b2s):
         _check(lib().cna_msca_equiv_kernel(_p(w1cat), _p(b1), _p(w2cat), _p(b2), ctypes.cast(ks_arr, c_void_p),
                                            len(ks), C, _p(weight), _p(bias), _p(res), _stream(weight)))
     return weight, bias, res
+
+
+def svd_topk(A: torch.Tensor, r: int, max_sweeps: int = 30):
+    """r leading singular triplets of a large fp32 matrix (either orientation) -> U (m,r), S (r), Vh (r,n)."""
+    _ready(A)
+    m, n = A.shape
+    if n > m:
+        U2, S, Vh2 = svd_topk(A.t().contiguous(), r, max_sweeps)
+        return Vh2.t().contiguous(), S, U2.t().contiguous()
+    Af = _f32c(A)
+    U = torch.empty((m, r), device=A.device, dtype=torch.float32)
+    S = torch.empty((r,), device=A.device, dtype=torch.float32)
+    Vh = torch.empty((r, n), device=A.device, dtype=torch.float32)
+    with torch.cuda.device(A.device):
+        _check(lib().cna_svd_jacobi_large(_p(Af), m, n, r, _p(U), _p(S), _p(Vh), max_sweeps, _stream(A)))
+    return U, S, Vh
+
+
+# ------------------------------------------------------------------------------------------- #
+# reconstruction step
+# ------------------------------------------------------------------------------------------- #
+def l2_recon(y_new, y_old, scale, want_grad=True):
+    """-> (norms (B,) fp32, grad like y_new or None): per-sample ||y_new - y_old||_2 and d(scale*sum_b norm_b)/dy_new."""
+    _ready(y_new)
+    assert y_new.shape == y_old.shape and y_new.dtype == y_old.dtype and y_new.is_contiguous() and y_old.is_contiguous()
+    Bn = y_new.shape[0]
+    per = y_new.numel() // Bn
+    scratch = torch.empty((Bn,), device=y_new.device, dtype=torch.float32)
+    norms = torch.empty((Bn,), device=y_new.device, dtype=torch.float32)
+    g = torch.empty_like(y_new) if want_grad else None
+    with torch.cuda.device(y_new.device):
+        _check(lib().cna_l2_recon_loss_grad(_p(y_new), _p(y_old), _p(scratch), _p(norms), _p(g), Bn, per, float(scale),
+                                            dtype_code(y_new.dtype), _stream(y_new)))
+    return norms, g
+
+
+def conv_taps_wgrad(x, g, taps, axis, pad, dw_out=None, db_out=None, want_bias=False):
+    """x (B,H,W,C), g (B,H,W,N) NHWC -> dw (N,C,taps) fp32 [, db (N,) fp32] for a stride-1 'same' tap conv."""
+    _ready(x)
+    Bn, H, W, C = x.shape
+    N = g.shape[3]
+    assert g.shape[:3] == x.shape[:3] and g.dtype == x.dtype and x.is_contiguous() and g.is_contiguous()
+    dw = torch.empty((N, C, taps), device=x.device, dtype=torch.float32) if dw_out is None else dw_out
+    db = None
+    if want_bias or db_out is not None:
+        db = torch.empty((N,), device=x.device, dtype=torch.float32) if db_out is None else db_out
+    with torch.cuda.device(x.device):
+        _check(lib().cna_conv_taps_wgrad(_p(x), _p(g), _p(dw), _p(db), Bn, H, W, C, N, taps, axis, pad,
+                                         dtype_code(x.dtype), _stream(x)))
+    return dw, db
+
+
+def pack_taps_dgrad(w, dtype):
+    """(O,I,kh,kw) tap-conv weight -> packed weight of the transposed conv: [taps][O][I] with flipped taps."""
+    _ready(w)
+    O, I, kh, kw = w.shape
+    taps = kh * kw
+    out = torch.empty((taps, O, I), device=w.device, dtype=dtype)
+    wf = _f32c(w)
+    with torch.cuda.device(w.device):
+        _check(lib().cna_pack_taps_weight_dgrad(_p(wf), _p(out), O, I, taps, dtype_code(dtype), _stream(w)))
+    return out
+
+
+def adamw_step_(param, grad, exp_avg, exp_avg_sq, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
+                grad_scale=1.0):
+    _ready(param)
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == param.numel()
+    with torch.cuda.device(param.device):
+        _check(lib().cna_adamw_step(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), float(lr),
+                                    float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step),
+                                    float(grad_scale), _stream(param)))
+    return param

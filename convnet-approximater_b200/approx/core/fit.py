@@ -71,3 +71,22 @@ def strip_factors(weight: torch.Tensor, rank: int):
     e = s ** 2
     pce = torch.mean(torch.sum(e[..., :rank], dim=-1) / torch.sum(e, dim=-1)).item()
     return out, pce
+
+
+def scheme2_svd(W: torch.Tensor, K: int):
+    """Conv weight (N,C,d,d) -> v_conv.weight (K,C,d,1), h_conv.weight (N,K,1,d): the closed-form scheme-2 fit
+    (Jaderberg et al. 2014, section 3.2): truncated SVD of A[(c,i),(j,n)] = W[n,c,i,j]; v = U*sqrt(S), h = sqrt(S)*Vh.
+    The reference has no scheme-2 app; this is the analogue of its scheme-1 SVD fit (core/low_rank_exp.py:110-120)."""
+    home = W.device
+    N, C, dh, dw = W.shape
+    A = _dev(W.detach()).to(torch.float32).permute(1, 2, 3, 0).reshape(C * dh, dw * N).contiguous()
+    r = min(K, C * dh, dw * N)
+    U, S, Vh = B.svd_topk(A, r)
+    sq = torch.sqrt(S)
+    v = torch.zeros(C * dh, K, device=A.device)
+    h = torch.zeros(K, dw * N, device=A.device)
+    v[:, :r] = U * sq[None, :]
+    h[:r, :] = Vh * sq[:, None]
+    v_w = v.reshape(C, dh, K).permute(2, 0, 1).unsqueeze(-1).contiguous()
+    h_w = h.reshape(K, dw, N).permute(2, 0, 1).unsqueeze(2).contiguous()
+    return v_w.to(home), h_w.to(home)

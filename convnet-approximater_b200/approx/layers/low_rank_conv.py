@@ -84,6 +84,44 @@ class LowRankExpConvV1(nn.Module):
         self.s_conv = sep
 
 
+class _Scheme2Function(torch.autograd.Function):
+    """Autograd bridge for the dense scheme-2 layer: forward = fused kernel, backward = this library's tap-conv
+    data / weight gradient kernels (what `total_loss.backward()` reaches in the reference's L2Reconstruct hook,
+    hooks/finetune.py:329-331).  T = v_conv(x) is recomputed in backward; the fused forward never stores it."""
+
+    @staticmethod
+    def forward(ctx, x, v_w, h_w, bias, mod):
+        H, W = x.shape[2:]
+        c_pad = B.round_up(mod.in_channels, 16) if mod._fusable(x.dtype, H, W) else None
+        xn = B.to_nhwc(x.detach(), c_pad)
+        y = mod.forward_nhwc(xn)
+        ctx.mod = mod
+        ctx.save_for_backward(xn)
+        return B.from_nhwc(y)
+
+    @staticmethod
+    def backward(ctx, gy):
+        mod = ctx.mod
+        (xn,) = ctx.saved_tensors
+        C, K = mod.in_channels, mod.num_base
+        kh, kw = mod.kernel_size
+        xg = xn if xn.shape[3] == C else xn[..., :C].contiguous()
+        g = B.to_nhwc(gy.to(xn.dtype)).contiguous()
+        t = _ops.dense_taps(mod.v_conv, xg)
+        dh, db = B.conv_taps_wgrad(t, g, kw, 1, mod.padding[1], want_bias=True)
+        wh_t = _ops.cached(mod.h_conv, "taps_w_dgrad", (mod.h_conv.weight,), xn.dtype,
+                           lambda: B.pack_taps_dgrad(mod.h_conv.weight, xn.dtype))
+        gt = B.conv_taps(g, wh_t, None, K, kw, 1, (1, 1), kw - 1 - mod.padding[1])
+        dv, _ = B.conv_taps_wgrad(xg, gt, kh, 0, mod.padding[0])
+        gx = None
+        if ctx.needs_input_grad[0]:
+            wv_t = _ops.cached(mod.v_conv, "taps_w_dgrad", (mod.v_conv.weight,), xn.dtype,
+                               lambda: B.pack_taps_dgrad(mod.v_conv.weight, xn.dtype))
+            gx = B.from_nhwc(B.conv_taps(gt, wv_t, None, C, kh, 0, (1, 1), kh - 1 - mod.padding[0]))
+        wd = mod.v_conv.weight.dtype
+        return gx, dv.view_as(mod.v_conv.weight).to(wd), dh.view_as(mod.h_conv.weight).to(wd), db.to(wd), None
+
+
 @LAYER.register_module()
 class LowRankExpConvV2(nn.Module):
     """Scheme 2: a dense vertical (d,1) conv into `num_base` = K channels (no bias) followed by a
@@ -142,8 +180,17 @@ class LowRankExpConvV2(nn.Module):
             raise RuntimeError("fuse_relu is only available with a dense h_conv (out_channels given)")
         return _ops.dw(self.h_conv, t)
 
+    def _trainable_here(self) -> bool:
+        kh, kw = self.kernel_size
+        return (self.dense and self.stride == (1, 1) and kh % 2 == 1 and kw % 2 == 1
+                and self.padding == (kh // 2, kw // 2))
+
     def forward(self, x):
         _ops.check_input(x)
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            if not self._trainable_here():
+                raise NotImplementedError("backward kernels cover the dense scheme-2 layer with stride 1 and 'same' padding")
+            return _Scheme2Function.apply(x, self.v_conv.weight, self.h_conv.weight, self.h_conv.bias, self)
         H, W = x.shape[2:]
         c_pad = B.round_up(self.in_channels, 16) if self._fusable(x.dtype, H, W) else None
         return B.from_nhwc(self.forward_nhwc(B.to_nhwc(x, c_pad)))

@@ -10,6 +10,9 @@
 //       - MscaRep.get_equivalent_kernel      reference src/approx/core/msca_rep.py:57-143
 #include "common.cuh"
 
+#include <algorithm>
+#include <vector>
+
 namespace cna {
 
 constexpr int kSvdMax = 64;   // max rows / cols handled by the in-smem Jacobi
@@ -165,6 +168,72 @@ __global__ void __launch_bounds__(256) lowrank1_factors_kernel(const float* __re
     }
 }
 
+// ---- one-sided Jacobi SVD of a large matrix, one launch per tournament round ---------------------------------
+// Work arrays (fp64): Wk [n][m] (row j = j-th column of A), Vk [n][n] (row j = j-th column of V).
+// Round `r` of the round-robin tournament pairs n/2 disjoint (p,q); each CTA orthogonalises one pair.
+__global__ void __launch_bounds__(256) jacobi_round_kernel(double* __restrict__ Wk, double* __restrict__ Vk, int m, int n,
+                                                          int n_even, int round, int* __restrict__ rotations) {
+    // round-robin schedule on n_even players (player n_even-1 fixed)
+    const int i = blockIdx.x;                 // 0 .. n_even/2 - 1
+    const int mod = n_even - 1;
+    int p, q;
+    if (i == 0) { p = n_even - 1; q = round % mod; }
+    else { p = (round + i) % mod; q = (round - i + mod) % mod; }
+    if (p >= n || q >= n) return;             // padding player
+    if (p > q) { int t = p; p = q; q = t; }
+    double* wp = Wk + (size_t)p * m; double* wq = Wk + (size_t)q * m;
+    double a = 0, b = 0, g = 0;
+    for (int k = threadIdx.x; k < m; k += 256) { double x = wp[k], y = wq[k]; a += x * x; b += y * y; g += x * y; }
+    __shared__ double red[3][8];
+    a = warp_sum(a); b = warp_sum(b); g = warp_sum(g);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = b; red[2][threadIdx.x >> 5] = g; }
+    __syncthreads();
+    a = b = g = 0;
+    for (int w = 0; w < 8; ++w) { a += red[0][w]; b += red[1][w]; g += red[2][w]; }
+    if (fabs(g) <= 1e-14 * sqrt(a * b) || g == 0.0) return;
+    if (threadIdx.x == 0) atomicAdd(rotations, 1);
+    double zeta = (b - a) / (2.0 * g);
+    double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+    double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+    for (int k = threadIdx.x; k < m; k += 256) { double x = wp[k], y = wq[k]; wp[k] = c * x - sn * y; wq[k] = sn * x + c * y; }
+    double* vp = Vk + (size_t)p * n; double* vq = Vk + (size_t)q * n;
+    for (int k = threadIdx.x; k < n; k += 256) { double x = vp[k], y = vq[k]; vp[k] = c * x - sn * y; vq[k] = sn * x + c * y; }
+}
+
+// A (m x n fp32 row-major) -> Wk [n][m] fp64 ; Vk = I
+__global__ void jacobi_init_kernel(const float* __restrict__ A, double* __restrict__ Wk, double* __restrict__ Vk, int m, int n) {
+    const long long tot = (long long)m * n;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
+        int j = (int)(i / m), k = (int)(i % m);
+        Wk[i] = (double)A[(size_t)k * n + j];
+    }
+    const long long tv = (long long)n * n;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < tv; i += (long long)gridDim.x * blockDim.x)
+        Vk[i] = (i / n == i % n) ? 1.0 : 0.0;
+}
+
+__global__ void jacobi_norms_kernel(const double* __restrict__ Wk, double* __restrict__ sv, int m, int n) {
+    const int j = blockIdx.x;
+    double a = 0;
+    for (int k = threadIdx.x; k < m; k += 256) { double x = Wk[(size_t)j * m + k]; a += x * x; }
+    __shared__ double red[8];
+    a = warp_sum(a);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0; for (int w = 0; w < 8; ++w) t += red[w]; sv[j] = sqrt(t); }
+}
+
+// gather the top-r triplets given the descending order: U (m x r), S (r), Vh (r x n), fp32
+__global__ void jacobi_gather_kernel(const double* __restrict__ Wk, const double* __restrict__ Vk, const double* __restrict__ sv,
+                                     const int* __restrict__ order, float* __restrict__ U, float* __restrict__ S,
+                                     float* __restrict__ Vh, int m, int n, int r) {
+    const int j = blockIdx.x, src = order[j];
+    const double s = sv[src];
+    for (int k = threadIdx.x; k < m; k += 256) U[(size_t)k * r + j] = (float)(s > 0 ? Wk[(size_t)src * m + k] / s : 0.0);
+    for (int k = threadIdx.x; k < n; k += 256) Vh[(size_t)j * n + k] = (float)Vk[(size_t)src * n + k];
+    if (threadIdx.x == 0) S[j] = (float)s;
+}
+
 struct EquivParams {
     int nb, C, K;
     int ks[kMaxBranches];
@@ -266,6 +335,54 @@ int cna_lowrank1_svd_fit(const float* W, int R, int q, int M, float* weights, fl
     lowrank1_factors_kernel<<<grid, 256, 0, st>>>(W, Vh, lam, weights, bases, R, q, M);
     CNA_LAUNCH_OK();
     CNA_CUDA(cudaFreeAsync(G, st));
+    return 0;
+}
+
+// Truncated SVD of a large fp32 matrix A (m x n row-major, n <= m): the r leading triplets.
+// One-sided (Hestenes) Jacobi in fp64 with a round-robin tournament: n-1 launches per sweep, n/2 independent column
+// pairs per launch; stops when a sweep makes no rotation.  Used for the scheme-2 closed-form fit, where A is the
+// (C*d) x (d*N) reshaping of the filter bank (Jaderberg et al. 2014, section 3.2).
+int cna_svd_jacobi_large(const float* A, int m, int n, int r, float* U, float* S, float* Vh, int max_sweeps, void* stream) {
+    CNA_CHECK(A && U && S && Vh, "null pointer");
+    CNA_CHECK(m >= n && n >= 1 && r >= 1 && r <= n, "need 1 <= r <= n <= m (transpose on the caller side otherwise)");
+    cudaStream_t st = as_stream(stream);
+    double *Wk = nullptr; int* d_rot = nullptr;
+    const size_t nW = (size_t)n * m, nV = (size_t)n * n;
+    CNA_CUDA(cudaMallocAsync(&Wk, (nW + nV + n) * sizeof(double), st));
+    CNA_CUDA(cudaMallocAsync(&d_rot, sizeof(int) * (n + 1), st));
+    double *Vk = Wk + nW, *sv = Vk + nV;
+    int* d_order = d_rot + 1;
+    jacobi_init_kernel<<<148 * 4, 256, 0, st>>>(A, Wk, Vk, m, n);
+    CNA_LAUNCH_OK();
+    const int n_even = n + (n & 1);
+    int sweeps = 0;
+    if (n > 1) {
+        for (; sweeps < max_sweeps; ++sweeps) {
+            CNA_CUDA(cudaMemsetAsync(d_rot, 0, sizeof(int), st));
+            for (int round = 0; round < n_even - 1; ++round)
+                jacobi_round_kernel<<<n_even / 2, 256, 0, st>>>(Wk, Vk, m, n, n_even, round, d_rot);
+            count_launch(n_even - 1);
+            int h_rot = 0;
+            CNA_CUDA(cudaMemcpyAsync(&h_rot, d_rot, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CNA_CUDA(cudaStreamSynchronize(st));
+            if (h_rot == 0) break;
+        }
+    }
+    jacobi_norms_kernel<<<n, 256, 0, st>>>(Wk, sv, m, n);
+    CNA_LAUNCH_OK();
+    // order by singular value (host side: n <= a few thousand values)
+    std::vector<double> h_sv(n);
+    CNA_CUDA(cudaMemcpyAsync(h_sv.data(), sv, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    CNA_CUDA(cudaStreamSynchronize(st));
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h_sv[a] > h_sv[b]; });
+    CNA_CUDA(cudaMemcpyAsync(d_order, order.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    jacobi_gather_kernel<<<r, 256, 0, st>>>(Wk, Vk, sv, d_order, U, S, Vh, m, n, r);
+    CNA_LAUNCH_OK();
+    CNA_CUDA(cudaStreamSynchronize(st));   // `order` (host) must outlive the copy
+    CNA_CUDA(cudaFreeAsync(Wk, st));
+    CNA_CUDA(cudaFreeAsync(d_rot, st));
     return 0;
 }
 

@@ -123,11 +123,37 @@ int cna_svd_small_batched(const float* A, float* U, float* S, float* Vh, int bat
  * bases (M,q) = sqrt(S)*Vh[:M]  (zero-filled beyond rank q).  Gram matrix + Jacobi eigen-solve in fp64.
  * Replaces numpy.linalg.svd + scaling at src/approx/core/low_rank_exp.py:110-120. */
 int cna_lowrank1_svd_fit(const float* W, int R, int q, int M, float* weights, float* bases, void* stream);
+/* Truncated SVD of a large fp32 matrix A (m x n row-major, n <= m): r leading triplets U (m,r), S (r), Vh (r,n).
+ * One-sided Jacobi in fp64, one launch per tournament round; synchronises the stream (fit-time call).
+ * Backs the scheme-2 closed-form fit W[n,c,i,j] ~ sum_k v[k,c,i] h[n,k,j] (no counterpart in the reference, which
+ * never shipped a scheme-2 app; the scheme-1 analogue is numpy.linalg.svd at src/approx/core/low_rank_exp.py:111). */
+int cna_svd_jacobi_large(const float* A, int m, int n, int r, float* U, float* S, float* Vh, int max_sweeps, void* stream);
 /* MSCA equivalent kernel (src/approx/core/msca_rep.py:57-143).  nb strip branches with odd sizes ks_host[i]
  * (ascending); w1cat / w2cat hold, branch after branch, the (C x k_i) row-major taps of conv1 (1 x k) and
  * conv2 (k x 1); b1 / b2 are (nb, C) or NULL.  Outputs: weight (C,K,K), bias (C), res (2,C,K/2), K = max k. */
 int cna_msca_equiv_kernel(const float* w1cat, const float* b1, const float* w2cat, const float* b2,
                           const int* ks_host, int nb, int C, float* weight, float* bias, float* res, void* stream);
+
+/* ---- reconstruction step ------------------------------------------------------------------------- */
+/* Per-sample output L2 error and the gradient of  scale * sum_b ||y_new_b - y_old_b||_2  w.r.t. y_new:
+ *   norms[b] = ||y_new_b - y_old_b||_2 ; grad = (y_new - y_old) * scale / norms[b]   (grad may be NULL: norms only).
+ * sumsq_scratch: B floats of workspace.  Replaces get_l2_error + the autograd of torch.norm / torch.mean at
+ * src/approx/hooks/finetune.py:80-82,315-322 (scale = l2_weight / (L * B_global)). */
+int cna_l2_recon_loss_grad(const void* y_new, const void* y_old, float* sumsq_scratch, float* norms, void* grad,
+                           int B, long long per_sample, float scale, int dtype, void* stream);
+/* Weight (and bias) gradient of a stride-1 'same' tap convolution (see cna_conv_taps_forward):
+ *   dw[o][i][t] = sum_p x[p shifted by tap t][i] * g[p][o]   (reference OIHW layout, fp32; overwritten)
+ *   dbias[o]    = sum_p g[p][o]                               (NULL to skip)
+ * Replaces autograd's conv backward-filter for v_conv / h_conv / 1x1 convs (src/approx/hooks/finetune.py:330). */
+int cna_conv_taps_wgrad(const void* x, const void* g, float* dw, float* dbias, int B, int H, int W, int C, int N,
+                        int taps, int axis, int pad, int dtype, void* stream);
+/* Packs w[o][i][t] for the INPUT gradient of a tap conv: packed[taps-1-t][o][i]; feed to cna_conv_taps_forward with
+ * C=O, N=I, pad = taps-1-pad to get dL/dx from dL/dy. */
+int cna_pack_taps_weight_dgrad(const float* w_oit, void* packed, int O, int I, int taps, int dtype, void* stream);
+/* Fused AdamW (torch.optim.AdamW semantics) on a flat fp32 buffer; grad is multiplied by grad_scale first
+ * (1/world_size after an all-reduce(SUM)).  Replaces optimizer.step() at src/approx/hooks/finetune.py:331. */
+int cna_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
 
 /* 2x2/stride-2 max pool, NHWC (VGG trunk glue between the approximated convs). */
 int cna_maxpool2x2(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream);

@@ -1,0 +1,176 @@
+"""Reconstruction step and scheme-2 fit on the GPU against torch autograd / the oracle on the same seeded inputs."""
+import copy
+
+import pytest
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from oracle import approx_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch_scheme2(C, K, N, seed):
+    torch.manual_seed(seed)
+    v = nn.Conv2d(C, K, (3, 1), 1, (1, 0), bias=False)
+    h = nn.Conv2d(K, N, (1, 3), 1, (0, 1))
+    return v, h
+
+
+def test_l2_recon_loss_and_grad():
+    from approx import backend as B
+    torch.manual_seed(0)
+    y_new = torch.randn(5, 7, 6, 9, requires_grad=True)
+    y_old = torch.randn(5, 7, 6, 9)
+    y_old[2] = y_new[2].detach()                       # zero-norm sample: gradient must be 0, not NaN
+    norms_ref = O.l2_recon_norm(y_new, y_old)
+    (0.3 * norms_ref.sum()).backward()
+    norms, g = B.l2_recon(y_new.detach().cuda(), y_old.cuda(), 0.3)
+    assert torch.allclose(norms.cpu(), norms_ref.detach(), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(g.cpu(), y_new.grad, rtol=1e-4, atol=1e-7)
+    assert torch.isfinite(g).all()
+
+
+@pytest.mark.parametrize("axis", [0, 1])
+@pytest.mark.parametrize("dims", [(2, 5, 9, 11, 7, 3), (3, 33, 8, 6, 70, 5), (1, 64, 14, 14, 64, 3)])
+def test_tap_conv_gradients_vs_autograd(axis, dims):
+    from approx import backend as B
+    Bn, C, H, W, N, taps = dims
+    torch.manual_seed(1)
+    x = torch.randn(Bn, C, H, W, requires_grad=True)
+    w = torch.randn(N, C, *((taps, 1) if axis == 0 else (1, taps)), requires_grad=True)
+    b = torch.randn(N, requires_grad=True)
+    pad = taps // 2
+    y = F.conv2d(x, w, b, 1, (pad, 0) if axis == 0 else (0, pad))
+    g = torch.randn_like(y)
+    y.backward(g)
+    xn, gn = B.to_nhwc(x.detach().cuda()).contiguous(), B.to_nhwc(g.cuda()).contiguous()
+    dw, db = B.conv_taps_wgrad(xn, gn, taps, axis, pad, want_bias=True)
+    assert torch.allclose(dw.cpu().reshape(w.shape), w.grad, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(db.cpu(), b.grad, rtol=1e-4, atol=1e-4)
+    wt = B.pack_taps_dgrad(w.detach().cuda(), torch.float32)
+    gx = B.conv_taps(gn, wt, None, C, taps, axis, (1, 1), taps - 1 - pad)
+    assert O.compare4d(x.grad, gx.permute(0, 3, 1, 2).cpu()) < 1e-5
+
+
+def test_adamw_matches_torch():
+    from approx import backend as B
+    torch.manual_seed(2)
+    p0 = torch.randn(1000)
+    p_ref = nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([p_ref], lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+    p = p0.clone().cuda(); m = torch.zeros_like(p); v = torch.zeros_like(p)
+    for step in range(1, 6):
+        g = torch.randn(1000)
+        p_ref.grad = g.clone()
+        opt.step()
+        B.adamw_step_(p, g.cuda(), m, v, step, 1e-2)
+    assert torch.allclose(p.cpu(), p_ref.detach(), rtol=1e-5, atol=1e-6)
+
+
+def _ref_steps(layer_state, C, K, N, xs, ys, lr, steps):
+    v, h = _torch_scheme2(C, K, N, 0)
+    v.weight.data = layer_state["v_conv.weight"].clone(); h.weight.data = layer_state["h_conv.weight"].clone()
+    h.bias.data = layer_state["h_conv.bias"].clone()
+    opt = torch.optim.AdamW(list(v.parameters()) + list(h.parameters()), lr=lr, weight_decay=0.01)
+    losses = []
+    for s in range(steps):
+        y = h(v(xs[s]))
+        loss = O.l2_recon_loss([O.l2_recon_norm(y, ys[s])])
+        opt.zero_grad(); loss.backward(); opt.step()
+        losses.append(loss.item())
+    return v, h, losses
+
+
+def test_reconstructor_matches_torch_training_fp32():
+    from approx.layers import LowRankExpConvV2
+    from approx.recon import Scheme2Reconstructor
+    C, K, N = 12, 6, 20
+    torch.manual_seed(3)
+    layer = LowRankExpConvV2(C, K, (3, 3), (1, 1), (1, 1), out_channels=N)
+    state = {k: v.clone() for k, v in layer.state_dict().items()}
+    teacher = nn.Conv2d(C, N, 3, 1, 1)
+    xs = [torch.randn(4, C, 10, 9) for _ in range(3)]
+    with torch.no_grad():
+        ys = [teacher(x) for x in xs]
+    v, h, losses = _ref_steps(state, C, K, N, xs, ys, 1e-2, 3)
+    layer = layer.cuda()
+    rec = Scheme2Reconstructor(layer, lr=1e-2)
+    from approx import backend as B
+    got = []
+    for x, y in zip(xs, ys):
+        got.append(rec.step(B.to_nhwc(x.cuda()).contiguous(), B.to_nhwc(y.cuda()).contiguous()).item())
+    assert torch.allclose(torch.tensor(got), torch.tensor(losses), rtol=1e-4)
+    assert torch.allclose(layer.v_conv.weight.cpu(), v.weight, rtol=1e-3, atol=2e-5)
+    assert torch.allclose(layer.h_conv.weight.cpu(), h.weight, rtol=1e-3, atol=2e-5)
+    assert torch.allclose(layer.h_conv.bias.cpu(), h.bias, rtol=1e-3, atol=2e-5)
+
+
+def test_reconstruction_reduces_error_bf16_fused_path():
+    """bf16 layer on the fused tcgen05 forward: the step must drive the per-sample output error down."""
+    from approx import backend as B
+    from approx.layers import LowRankExpConvV2
+    from approx.recon import Scheme2Reconstructor
+    torch.manual_seed(4)
+    C, K, N = 64, 16, 64
+    teacher = nn.Conv2d(C, N, 3, 1, 1).cuda().bfloat16()
+    layer = LowRankExpConvV2(C, K, (3, 3), (1, 1), (1, 1), out_channels=N).cuda().bfloat16()
+    rec = Scheme2Reconstructor(layer, lr=5e-3)
+    x = torch.randn(8, C, 28, 28, device="cuda").bfloat16()
+    with torch.no_grad():
+        y = teacher(x)
+    xn, yn = B.to_nhwc(x).contiguous(), B.to_nhwc(y).contiguous()
+    first = rec.step(xn, yn).item()
+    for _ in range(40):
+        last = rec.step(xn, yn).item()
+    assert last < 0.9 * first
+
+
+def test_module_autograd_bridge():
+    from approx.layers import LowRankExpConvV2
+    torch.manual_seed(5)
+    C, K, N = 8, 4, 16
+    layer = LowRankExpConvV2(C, K, (3, 3), (1, 1), (1, 1), out_channels=N)
+    v, h = _torch_scheme2(C, K, N, 0)
+    v.weight.data = layer.v_conv.weight.data.clone(); h.weight.data = layer.h_conv.weight.data.clone()
+    h.bias.data = layer.h_conv.bias.data.clone()
+    x = torch.randn(3, C, 9, 7)
+    xr = x.clone().requires_grad_(True)
+    tgt = torch.randn(3, N, 9, 7)
+    loss_ref = torch.mean(O.l2_recon_norm(h(v(xr)), tgt)); loss_ref.backward()
+    layer = layer.cuda()
+    xg = x.cuda().requires_grad_(True)
+    loss = torch.mean(torch.norm((layer(xg) - tgt.cuda()).reshape(3, -1), p=2, dim=1)); loss.backward()
+    assert abs(loss.item() - loss_ref.item()) < 1e-5
+    assert torch.allclose(layer.v_conv.weight.grad.cpu(), v.weight.grad, rtol=1e-3, atol=1e-6)
+    assert torch.allclose(layer.h_conv.weight.grad.cpu(), h.weight.grad, rtol=1e-3, atol=1e-6)
+    assert torch.allclose(layer.h_conv.bias.grad.cpu(), h.bias.grad, rtol=1e-3, atol=1e-6)
+    assert O.compare4d(xr.grad, xg.grad.cpu()) < 1e-5
+
+
+def test_svd_topk_and_scheme2_fit():
+    from approx import backend as B
+    from approx.core import LowRankExpV2
+    torch.manual_seed(6)
+    A = torch.randn(90, 60)
+    U, S, Vh = B.svd_topk(A.cuda(), 60)
+    assert torch.allclose((U * S) @ Vh, A.cuda(), atol=1e-4)
+    assert torch.allclose(S.cpu(), torch.linalg.svdvals(A), rtol=1e-5, atol=1e-5)
+    U, S, Vh = B.svd_topk(A.t().contiguous().cuda(), 10)        # wide orientation, truncated
+    best = torch.linalg.svd(A.t(), full_matrices=False)
+    assert torch.allclose(((U * S) @ Vh).cpu(), (best[0][:, :10] * best[1][:10]) @ best[2][:10], atol=1e-4)
+    # app flow: full-rank fit reproduces the source conv, truncated fit matches the oracle's closed form
+    src = nn.Conv2d(6, 10, 3, 1, 1)
+    x = torch.randn(2, 6, 9, 8)
+    for K in (18, 5):
+        app = LowRankExpV2(num_bases=(K,))
+        sub = app.initialize(src)
+        app.optimize(sub)
+        tgt = app.postprocess(sub)
+        v_o, h_o = O.lowrank2_svd_fit(src.weight.data, K)
+        ref = O.lowrank2_forward(x, v_o, h_o, src.bias.data, (1, 1), (1, 1))
+        y = tgt.cuda()(x.cuda())
+        assert O.compare4d(ref, y.detach().cpu()) < 2e-5
+        if K == 18:
+            assert O.compare4d(src(x).detach(), y.detach().cpu()) < 2e-5

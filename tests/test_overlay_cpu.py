@@ -1,0 +1,68 @@
+"""Overlay (drop-in) mode: with CNA_REFERENCE_SRC set, the reference's own model / filter / config code runs on top of
+this backend's `approx.layers` and `approx.core`.  Needs the reference tree, which exists only in the build container
+(skipped elsewhere); CPU only, so it checks structure — registration, substitution, state_dict keys — and that the
+layers in place are this backend's (their forward refuses CPU tensors)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+REF = "/root/reference/src"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SCRIPT = r'''
+import sys, types
+for name in ("timm", "timm.data", "timm.models", "timm.utils", "timm.loss", "timm.optim", "timm.scheduler", "ptflops"):
+    sys.modules.setdefault(name, types.ModuleType(name))
+import torch
+import approx.layers, approx.core
+from approx.models import build_model, MODEL
+from approx.core import build_app
+from approx.filters import build_filter
+from approx.utils import init_cfg, get_cfg
+assert approx.layers.__file__.startswith(sys.argv[1]), approx.layers.__file__
+import approx.models.switchable as sw
+assert sw.__file__.startswith("/root/reference"), sw.__file__
+init_cfg("/root/reference/configs/msca-rep/msca-rep_d1_fix_mscan-t.py")
+cfg = get_cfg()
+model = build_model(dict(cfg.model, init_cfg=None))
+app = build_app(cfg.app, deploy=False)
+filters = [build_filter(f) for f in (cfg.filters or [])]
+model.register_switchable(app.src_type, filters)
+assert model.length_switchable == 13
+for idx in range(model.length_switchable):
+    src = model.get_switchable_module(idx)
+    model.set_switchable_module(idx, app.initialize, src=src)
+sub = model.get_switchable_module(0)
+assert type(sub).__module__ == "approx.layers.substituton"
+keys = [k for k in model.state_dict() if ".new.sd_convs" in k and "block.0" in k or ".new.sd_convs" in k]
+assert any(k.endswith("new.sd_convs.0.conv1.weight") for k in keys) and any(k.endswith("new.sd_convs.1.res") for k in keys)
+try:
+    sub.new(torch.randn(1, 32, 8, 8))
+    raise SystemExit("expected the backend to refuse a CPU tensor")
+except RuntimeError as e:
+    assert "no CPU fallback" in str(e)
+# low-rank config through the reference's AlexNet + SimpleConvFilter + IndicesFilter
+init_cfg("/root/reference/configs/low-rank-exp/low-rank-exp-v1_l2345_svd_dodecomp_alexnet.py")
+cfg = get_cfg()
+model = build_model(dict(cfg.model, init_cfg=None))
+app = build_app(cfg.app, deploy=False)
+filters = [build_filter(f) for f in cfg.filters]
+model.register_switchable(app.src_type, filters)
+assert model.length_switchable == 4
+for idx in range(4):
+    model.set_switchable_module(idx, app.initialize, src=model.get_switchable_module(idx))
+names = [type(model.get_switchable_module(i).new).__name__ for i in range(4)]
+assert names == ["LowRankExpConvV1"] * 4
+print("overlay ok")
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present on this machine")
+def test_reference_models_and_configs_drive_this_backend():
+    env = dict(os.environ, CNA_REFERENCE_SRC=REF, PYTHONPATH=os.path.join(ROOT, "convnet-approximater_b200"))
+    pkg = os.path.join(ROOT, "convnet-approximater_b200")
+    out = subprocess.run([sys.executable, "-c", SCRIPT, pkg], env=env, capture_output=True, text=True, cwd="/tmp", timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "overlay ok" in out.stdout

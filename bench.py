@@ -3,8 +3,8 @@
 
 Workload (configs[1]): the VGG-16 convolutional trunk with all 13 3x3 convs replaced by scheme-2
 low-rank expansions (rank K each, default 64), bf16 inference, batch 256 at 224x224 per GPU, each conv
-ONE fused tcgen05 kernel (v_conv -> bf16 T in shared memory -> h_conv + bias + ReLU), 2x2 max-pools
-between stages.  A "step" is one forward pass of that trunk over one batch of synthetic images.
+ONE fused tcgen05 kernel (v_conv -> bf16 T in shared memory -> h_conv + bias + ReLU [+ VGG's 2x2 max-pool on the 5
+layers it follows]).  A "step" is one forward pass of that trunk over one batch of synthetic images.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--rank K] [--batch B]
 
@@ -33,12 +33,18 @@ VGG = [(3, 64, 224), (64, 64, 224), (64, 128, 112), (128, 128, 112), (128, 256, 
 METRIC = "approx-conv images/sec (224^2, VGG-16 trunk, 13 scheme-2 low-rank convs)"
 
 
-def algorithmic_bytes_per_image(K, c_in_first=3):
-    """per scheme-2 layer 2*(H*W*C + H*W*N) activation bytes + 2*d*K*(C+N) weight bytes + 2N bias."""
-    tot = 0
-    for (C, N, H) in VGG:
-        tot += 2 * H * H * (C + N) + 2 * 3 * K * (C + N) + 2 * N
-    return tot
+POOLED = {1, 3, 6, 9, 12}     # convs followed by VGG's 2x2 max-pool (fused into their epilogue: they write H*W/4 pixels)
+
+
+def layer_bytes(i, K):
+    """Algorithmic HBM bytes of layer i per image: bf16 input + output actually written + weights + bias."""
+    C, N, H = VGG[i]
+    out_px = H * H // 4 if i in POOLED else H * H
+    return 2 * H * H * C + 2 * out_px * N + 2 * 3 * K * (C + N) + 2 * N
+
+
+def algorithmic_bytes_per_image(K):
+    return sum(layer_bytes(i, K) for i in range(len(VGG)))
 
 
 def algorithmic_flops_per_image(K):
@@ -176,17 +182,12 @@ def run_ours(args):
           for _ in range(args.steps)]
 
     def step(x, events=None):
-        i = 0
-        for m in trunk.features:
-            if isinstance(m, torch.nn.Identity):
-                x = B.maxpool2x2(x)
-            else:
-                if events is not None:
-                    events[i][0].record()
-                x = m.forward_nhwc(x)
-                if events is not None:
-                    events[i][1].record()
-                i += 1
+        for i, m in enumerate(trunk.features):
+            if events is not None:
+                events[i][0].record()
+            x = m.forward_nhwc(x)
+            if events is not None:
+                events[i][1].record()
         return x
 
     def sync_all():
@@ -266,7 +267,7 @@ def run_ours(args):
         if args.per_layer:
             for i, (C, N, H) in enumerate(VGG):
                 lms = sum(ev[s_][i][0].elapsed_time(ev[s_][i][1]) for s_ in range(args.steps)) / args.steps
-                lb = (2 * H * H * (C + N) + 6 * K * (C + N) + 2 * N) * Bsz
+                lb = layer_bytes(i, K) * Bsz
                 lf = (6 * H * H * K * (C + N)) * Bsz
                 sys.stderr.write(f"layer {i + 1:2d} {C:3d}->{N:3d} @{H:3d}: {lms:7.3f} ms  {lb / lms / 1e6:7.0f} GB/s "
                                  f"({lb / lms / 1e6 / hbm_peak:5.1%} of HBM peak)  {lf / lms / 1e9:6.0f} TFLOP/s\n")

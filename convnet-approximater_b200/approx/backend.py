@@ -30,8 +30,9 @@ _SIGS = {
     "cna_fix_padding_bias": "ppiiiiiip",
     "cna_add": "pppLip",
     "cna_lowrank2_pack": "ppppiiiiiip",
-    "cna_lowrank2_fused_forward": "pppppiiiiiiiip",
+    "cna_lowrank2_fused_forward": "pppppiiiiiiiiip",
     "cna_lowrank2_fused_supported": "iiiiii",
+    "cna_lowrank2_fused_forward_traced": "pppppiiiiiiiippi",
     "cna_maxpool2x2": "ppiiiiip",
     "cna_msca_sd_supported": "iiipi",
     "cna_msca_sd_forward": "pppppppppipiiiiiiip",
@@ -312,17 +313,31 @@ def lowrank2_pack(v_w, h_w):
     return wv, wh
 
 
-def lowrank2_fused(x, wv, wh, bias, relu=False):
-    """x (B,H,W,c_pad) bf16 NHWC -> (B,H,W,N) bf16; stride 1, 'same' padding."""
+def lowrank2_fused_traced(x, wv, wh, bias, tiles=32, relu=False):
+    """Diagnostic: like lowrank2_fused, also returns a (tiles, 10) int64 tensor of CTA-0 clock stamps."""
+    _ready(x)
+    Bn, H, W, cp = x.shape
+    d, kp, _ = wv.shape
+    N = wh.shape[1]
+    y = torch.empty((Bn, H, W, N), device=x.device, dtype=torch.bfloat16)
+    trace = torch.zeros((tiles, 10), device=x.device, dtype=torch.int64)
+    with torch.cuda.device(x.device):
+        _check(lib().cna_lowrank2_fused_forward_traced(_p(x), _p(wv), _p(wh), _p(bias), _p(y), Bn, H, W, cp, kp, N, d,
+                                                       int(relu), _stream(x), _p(trace), tiles))
+    return y, trace
+
+
+def lowrank2_fused(x, wv, wh, bias, relu=False, pool=False):
+    """x (B,H,W,c_pad) bf16 NHWC -> (B,H,W,N) bf16 (or (B,H/2,W/2,N) with the fused 2x2 max-pool); stride 1, 'same'."""
     _ready(x)
     B, H, W, cp = x.shape
     d, kp, cp2 = wv.shape
     N = wh.shape[1]
     assert cp == cp2 and x.dtype == torch.bfloat16 and x.is_contiguous()
-    y = torch.empty((B, H, W, N), device=x.device, dtype=torch.bfloat16)
+    y = torch.empty((B, H // 2, W // 2, N) if pool else (B, H, W, N), device=x.device, dtype=torch.bfloat16)
     with torch.cuda.device(x.device):
         _check(lib().cna_lowrank2_fused_forward(_p(x), _p(wv), _p(wh), _p(bias), _p(y), B, H, W, cp, kp, N, d,
-                                                int(relu), _stream(x)))
+                                                int(relu), int(pool), _stream(x)))
     return y
 
 

@@ -148,6 +148,7 @@ class LowRankExpConvV2(nn.Module):
         else:
             self.h_conv = nn.Conv2d(num_base, out_channels, (1, kernel_size[1]), (1, stride[1]), (0, padding[1]))
         self.fuse_relu = False  # set by callers that own the following ReLU (VGG trunk)
+        self.fuse_pool = False  # ... and the following 2x2 max-pool (fused kernel only)
 
     @property
     def bias(self):
@@ -172,10 +173,13 @@ class LowRankExpConvV2(nn.Module):
                 raise ValueError(f"fused path wants {c_pad} input channels (zero padded), got {cx}")
             wv, wh = _ops.cached(self, "lr2_pack", (self.v_conv.weight, self.h_conv.weight), torch.bfloat16,
                                  lambda: B.lowrank2_pack(self.v_conv.weight, self.h_conv.weight))
-            return B.lowrank2_fused(x, wv, wh, _ops.bias_f32(self.h_conv), relu=self.fuse_relu)
+            pool = self.fuse_pool and H % 2 == 0 and W % 2 == 0
+            y = B.lowrank2_fused(x, wv, wh, _ops.bias_f32(self.h_conv), relu=self.fuse_relu, pool=pool)
+            return B.maxpool2x2(y) if self.fuse_pool and not pool else y
         t = _ops.dense_taps(self.v_conv, x)
         if self.dense:
-            return _ops.dense_taps(self.h_conv, t, relu=self.fuse_relu)
+            y = _ops.dense_taps(self.h_conv, t, relu=self.fuse_relu)
+            return B.maxpool2x2(y) if self.fuse_pool else y
         if self.fuse_relu:
             raise RuntimeError("fuse_relu is only available with a dense h_conv (out_channels given)")
         return _ops.dw(self.h_conv, t)

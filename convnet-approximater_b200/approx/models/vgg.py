@@ -3,7 +3,8 @@
 The reference ships AlexNet and MSCAN only; BASELINE.json's headline configuration ("VGG-16, all 3x3
 conv layers replaced by scheme-2 low-rank expansions, bf16 inference, batch 256 at 224x224") is built
 here from the same layer class the registry exposes (`LowRankExpConvV2` with a dense h_conv).
-The trunk runs NHWC end to end: 13 fused low-rank convs (ReLU in their epilogue) and 5 2x2 max-pools.
+The trunk runs NHWC end to end: 13 fused low-rank convs with ReLU — and, on the 5 layers VGG pools after, the
+2x2 max-pool — fused into the kernel's epilogue.
 """
 from typing import Sequence, Union
 
@@ -26,13 +27,13 @@ class VGG16Scheme2Trunk(nn.Module):
         assert len(ranks) == len(convs)
         self.features = nn.ModuleList()
         it = iter(ranks)
-        for c in VGG16_CFG:
+        for i, c in enumerate(VGG16_CFG):
             if c == "M":
-                self.features.append(nn.Identity())  # placeholder: pooling is done by the backend kernel
-            else:
-                layer = LowRankExpConvV2(c[0], next(it), (3, 3), (1, 1), (1, 1), out_channels=c[1])
-                layer.fuse_relu = True
-                self.features.append(layer)
+                continue                       # the pool is fused into the preceding conv's epilogue
+            layer = LowRankExpConvV2(c[0], next(it), (3, 3), (1, 1), (1, 1), out_channels=c[1])
+            layer.fuse_relu = True
+            layer.fuse_pool = i + 1 < len(VGG16_CFG) and VGG16_CFG[i + 1] == "M"
+            self.features.append(layer)
 
     def conv_layers(self):
         return [m for m in self.features if isinstance(m, LowRankExpConvV2)]
@@ -40,7 +41,7 @@ class VGG16Scheme2Trunk(nn.Module):
     def forward_nhwc(self, x):
         """x: (B,H,W,16) bf16 (3 image channels zero-padded to 16) or (B,H,W,3) fp32."""
         for m in self.features:
-            x = B.maxpool2x2(x) if isinstance(m, nn.Identity) else m.forward_nhwc(x)
+            x = m.forward_nhwc(x)
         return x
 
     def forward(self, x):

@@ -37,7 +37,7 @@
 namespace cna {
 using namespace ptx;
 
-constexpr int kThreads = 320;        // warp 0 TMA, warp 1 MMA, warps 2-5 T-epilogue, warps 6-9 Y-epilogue
+constexpr int kThreads = 352;        // warp 0 TMA, warp 1 GEMM1 issuer, warps 2-5 T-epilogue, 6-9 Y-epilogue, warp 10 GEMM2 issuer
 constexpr int kTileRows = 8;           // output rows per tile
 constexpr int kTileCols = 16;          // computed columns per tile (14 valid + 2 halo)
 constexpr int kValidCols = kTileCols - 2;
@@ -50,6 +50,7 @@ constexpr int kMaxNTiles = 16;         // N <= 1024
 // T lives in the NO-swizzle K-major UMMA layout: 8-slot groups of 16-byte chunks, group pitch kTSbo, chunk-plane
 // pitch kTLbo.  The 144-byte group pitch (instead of 128) makes the transposing epilogue stores — 8 lanes that
 // hit 8 consecutive groups at the same in-group row — fall into 8 different bank quads.
+constexpr int kTraceEv = 10;
 constexpr uint32_t kTSbo = 144;
 constexpr uint32_t kTLbo = kTCols * kTSbo;   // 2592
 
@@ -62,13 +63,17 @@ struct LR2Params {
     int stages;            // x ring depth
     int resident;          // 1: all weights stay in smem for the whole kernel; 0: streamed per tile
     int relu;
+    int pool;              // fuse a 2x2/stride-2 max-pool into the epilogue (y is then [B, H/2, W/2, N])
     // smem byte offsets from the 1024-aligned base
     uint32_t off_x, x_stage;      // x ring
     uint32_t off_v, v_chunk;      // Wv chunks (resident: nch of them; streamed: one per x stage)
     uint32_t off_h, h_tile;       // Wh N-tiles (resident: nnt; streamed: 2)
     uint32_t off_t, t_buf;        // T buffers (2)
     uint32_t off_y, y_buf;        // y staging (2)
+    uint32_t off_p;               // pooled staging (2 x 4 KB), only when pool
     uint32_t off_bias, off_bar;
+    long long* trace;      // diagnostic: per-tile clock64() stamps of CTA 0 (NULL = off), kTraceEv slots per tile
+    int trace_tiles;
 };
 
 __host__ __device__ constexpr uint32_t swz_type(int row_bytes) { return row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u); }
@@ -115,7 +120,7 @@ template <int CK, int KP>
 __global__ void __launch_bounds__(kThreads, 1)
 lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_wv,
                       const __grid_constant__ CUtensorMap tm_wh, const __grid_constant__ CUtensorMap tm_y,
-                      const float* __restrict__ bias, const LR2Params p) {
+                      const float* __restrict__ bias, const LR2Params p) {   // tm_y describes the pooled tensor when p.pool
     constexpr int XROW = CK * 2;            // bytes per x / Wv smem row (== swizzle span)
     constexpr int HROW = KP * 2;            // bytes per Wh smem row
     constexpr int TCH = KP / 8;             // 16-byte chunks per T slot
@@ -159,6 +164,9 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
 
     const int first = blockIdx.x, step = gridDim.x;
     const int my_tiles = first < p.ntiles ? (p.ntiles - first + step - 1) / step : 0;
+    auto stamp = [&](int it, int ev) {
+        if (p.trace != nullptr && blockIdx.x == 0 && it < p.trace_tiles) p.trace[it * kTraceEv + ev] = clock64();
+    };
 
     if (warp == 0) {
         // =========================== TMA producer ===========================
@@ -191,6 +199,7 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                     __syncwarp();
                     if (++xs == p.stages) { xs = 0; xph ^= 1u; }
                 }
+                if (lane == 0) stamp(it, 0);
             };
             auto load_h = [&]() {
                 if (p.resident) return;
@@ -214,24 +223,25 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             }
         }
     } else if (warp == 1) {
-        // =========================== MMA issuer ===========================
+        // =========================== GEMM1 issuer ===========================
+        // Two issuing warps (GEMM1 here, GEMM2 in warp 10): UTCHMMA issue blocks while the tensor pipe's short queue
+        // is full, so a single issuer would expose every mbarrier wait (~100-200 cycles each, ~1350 per tile measured
+        // with benchmarks/trace_lowrank2.py) as pipe idle time; with two, one warp's waits overlap the other's MMAs.
         if (my_tiles > 0) {
             constexpr uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KP >> 3) << 17) | (8u << 24);
-            constexpr uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kNT >> 3) << 17) | (8u << 24);
             constexpr uint64_t xdesc = desc_hi(16, 8 * XROW, swz_type(XROW));     // x tile and Wv chunk (swizzled, K-major)
-            constexpr uint64_t hdesc = desc_hi(16, 8 * HROW, swz_type(HROW));     // Wh tile
-            constexpr uint64_t tdesc = desc_hi(kTLbo, kTSbo, 0);                  // T: no-swizzle K-major
             int xs = 0; uint32_t xph = 0;
-            int q = 0;   // N-tile counter (Y accumulator / Wh ring index)
             if (p.resident) { mbar_wait(bar(BAR_WFULL), 0); tc_fence_after_sync(); }
-            auto gemm1 = [&](int it) {
+            for (int it = 0; it < my_tiles; ++it) {
                 const int buf = it & 1;
+                if (lane == 0) stamp(it, 1);
                 mbar_wait(bar(BAR_TACC_EMPTY + buf), (uint32_t)((it >> 1) & 1) ^ 1u);
                 tc_fence_after_sync();
                 const uint32_t d = tmem_T + buf * 64;
                 for (int ch = 0; ch < p.nch; ++ch) {
                     mbar_wait(bar(BAR_XFULL + xs), xph);
                     tc_fence_after_sync();
+                    if (lane == 0 && ch == 0) stamp(it, 2);
                     const uint64_t a0 = xdesc + ((base + p.off_x + xs * p.x_stage) >> 4);
                     const uint64_t b0 = xdesc + ((base + p.off_v + (p.resident ? ch : xs) * p.v_chunk) >> 4);
                     if (elect_one()) {
@@ -247,11 +257,23 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                     __syncwarp();
                     if (++xs == p.stages) { xs = 0; xph ^= 1u; }
                 }
-            };
-            auto gemm2 = [&](int j) {
+                if (lane == 0) stamp(it, 3);
+            }
+        }
+    } else if (warp == 10) {
+        // =========================== GEMM2 issuer ===========================
+        if (my_tiles > 0) {
+            constexpr uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kNT >> 3) << 17) | (8u << 24);
+            constexpr uint64_t hdesc = desc_hi(16, 8 * HROW, swz_type(HROW));     // Wh tile
+            constexpr uint64_t tdesc = desc_hi(kTLbo, kTSbo, 0);                  // T: no-swizzle K-major
+            int q = 0;   // N-tile counter (Y accumulator / Wh ring index)
+            if (p.resident) { mbar_wait(bar(BAR_WFULL), 0); tc_fence_after_sync(); }
+            for (int j = 0; j < my_tiles; ++j) {
                 const int buf = j & 1;
+                if (lane == 0) stamp(j, 4);
                 mbar_wait(bar(BAR_TSM_FULL + buf), (uint32_t)((j >> 1) & 1));
                 tc_fence_after_sync();
+                if (lane == 0) stamp(j, 5);
                 const uint64_t a0 = tdesc + ((base + p.off_t + buf * p.t_buf) >> 4);
                 for (int nt = 0; nt < p.nnt; ++nt, ++q) {
                     const int yb = q & 1;
@@ -280,11 +302,6 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                     }
                     __syncwarp();
                 }
-            };
-            gemm1(0);
-            for (int it = 0; it < my_tiles; ++it) {
-                if (it + 1 < my_tiles) gemm1(it + 1);
-                gemm2(it);
             }
         }
     } else if (warp < 6) {
@@ -300,6 +317,7 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             const uint32_t ph = (uint32_t)((it >> 1) & 1);
             mbar_wait(bar(BAR_TACC_FULL + buf), ph);
             tc_fence_after_sync();
+            if (threadIdx.x == 64) stamp(it, 6);
             uint32_t v[KP];
 #pragma unroll
             for (int c16 = 0; c16 < KP / 16; ++c16) tmem_ld16(tmem_T + buf * 64 + lane_addr + c16 * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[c16 * 16]));
@@ -317,8 +335,9 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                              pack_bf16(__uint_as_float(v[ch * 8 + 6]), __uint_as_float(v[ch * 8 + 7])));
             fence_proxy_async_smem();
             mbar_arrive(bar(BAR_TSM_FULL + buf));
+            if (threadIdx.x == 64) stamp(it, 7);
         }
-    } else {
+    } else if (warp < 10) {
         // =========================== Y-epilogue warps (6..9) ===========================
         // TMEM accumulator of GEMM2 -> +bias, ReLU -> bf16 -> swizzled staging -> TMA store.
         const int lg = warp & 3;
@@ -338,6 +357,7 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 const uint32_t sb = base + p.off_y + yb * p.y_buf;
                 mbar_wait(bar(BAR_YACC_FULL + yb), (uint32_t)((q >> 1) & 1));
                 tc_fence_after_sync();
+                if (et == 0 && nt == 0) stamp(j, 8);
                 uint32_t v[kNT];
 #pragma unroll
                 for (int c16 = 0; c16 < kNT / 16; ++c16) tmem_ld16(tmem_Y + yb * 64 + lane_addr + c16 * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[c16 * 16]));
@@ -359,11 +379,51 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                         st_shared_v4(sb + row_off + (((uint32_t)ch ^ sw) << 4), w0, w1, w2, w3);
                     }
                 }
-                fence_proxy_async_smem();
-                named_bar_sync(2, 128);
-                if (et == 0) {
-                    tma_store_4d(&tm_y, sb, nt * kNT, t.w0, t.h0, t.b);
-                    tma_store_commit();
+                if (!p.pool) {
+                    fence_proxy_async_smem();
+                    named_bar_sync(2, 128);
+                    if (et == 0) {
+                        tma_store_4d(&tm_y, sb, nt * kNT, t.w0, t.h0, t.b);
+                        tma_store_commit();
+                        if (nt == p.nnt - 1) stamp(j, 9);
+                    }
+                } else {
+                    // 2x2 max-pool of the staged 8 x 14 tile -> 4 x 7 pooled tile (bf16 max commutes with the rounding)
+                    named_bar_sync(2, 128);
+                    const uint32_t pb = base + p.off_p + yb * 4096;
+#pragma unroll
+                    for (int rep = 0; rep < 2; ++rep) {
+                        const int id = et + rep * 128;            // 28 pooled pixels x 8 chunks of 16 bytes
+                        if (id < 28 * 8) {
+                            const int pp = id >> 3, ch = id & 7, pr = pp / 7, pc = pp - pr * 7;
+                            uint4 m4 = make_uint4(0, 0, 0, 0);
+#pragma unroll
+                            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                                for (int bq = 0; bq < 2; ++bq) {
+                                    const uint32_t row = (uint32_t)((2 * pr + a) * kValidCols + 2 * pc + bq);
+                                    uint4 v4;
+                                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                                 : "=r"(v4.x), "=r"(v4.y), "=r"(v4.z), "=r"(v4.w)
+                                                 : "r"(sb + row * 128u + (((uint32_t)ch ^ (row & 7u)) << 4)));
+                                    if (a == 0 && bq == 0) m4 = v4;
+                                    else {
+                                        __nv_bfloat162* mm = reinterpret_cast<__nv_bfloat162*>(&m4);
+                                        const __nv_bfloat162* vv = reinterpret_cast<const __nv_bfloat162*>(&v4);
+#pragma unroll
+                                        for (int e = 0; e < 4; ++e) mm[e] = __hmax2(mm[e], vv[e]);
+                                    }
+                                }
+                            st_shared_v4(pb + (uint32_t)pp * 128u + (((uint32_t)ch ^ ((uint32_t)pp & 7u)) << 4), m4.x, m4.y, m4.z, m4.w);
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(3, 128);
+                    if (et == 0) {
+                        tma_store_4d(&tm_y, pb, nt * kNT, t.w0 >> 1, t.h0 >> 1, t.b);
+                        tma_store_commit();
+                        if (nt == p.nnt - 1) stamp(j, 9);
+                    }
                 }
             }
         }
@@ -439,13 +499,14 @@ static uint32_t up1k(uint32_t v) { return (v + 1023u) & ~1023u; }
 
 // Fills the smem plan; returns total dynamic smem bytes (incl. 1 KB alignment slack) or 0 if it cannot fit.
 static size_t plan_smem(LR2Params& p, int CK, int KP, size_t limit) {
+    const uint32_t pool_bytes = p.pool ? 2 * 4096 : 0;
     const uint32_t xrow = CK * 2, trow = KP * 2;
     p.x_stage = up1k(kXRows * kTileCols * xrow);
     p.v_chunk = up1k(3 * KP * xrow);
     p.h_tile = up1k(3 * kNT * trow);
     p.t_buf = up1k((KP / 8) * kTLbo);
     p.y_buf = 16384;
-    const uint32_t fixed = 2 * p.t_buf + 2 * p.y_buf + up1k(p.N * 4) + 1024 /*barriers*/ + 1024 /*align slack*/;
+    const uint32_t fixed = 2 * p.t_buf + 2 * p.y_buf + pool_bytes + up1k(p.N * 4) + 1024 /*barriers*/ + 1024 /*align slack*/;
     for (int resident = 1; resident >= 0; --resident) {
         for (int stages = kMaxStages; stages >= 2; --stages) {
             uint32_t vbytes = (resident ? p.nch : stages) * p.v_chunk;
@@ -460,6 +521,7 @@ static size_t plan_smem(LR2Params& p, int CK, int KP, size_t limit) {
                 p.off_h = o; o += hbytes;
                 p.off_t = o; o += 2 * p.t_buf;
                 p.off_y = o; o += 2 * p.y_buf;
+                p.off_p = o; o += pool_bytes;
                 p.off_bias = o; o += up1k(p.N * 4);
                 p.off_bar = o;
                 return total;
@@ -500,8 +562,9 @@ int cna_lowrank2_pack(const float* v_w, const float* h_w, void* wv_packed, void*
     return 0;
 }
 
-int cna_lowrank2_fused_forward(const void* x, const void* wv_packed, const void* wh_packed, const float* bias, void* y,
-                               int B, int H, int W, int c_pad, int k_pad, int N, int d, int relu, void* stream) {
+static int lr2_launch(const void* x, const void* wv_packed, const void* wh_packed, const float* bias, void* y,
+                      int B, int H, int W, int c_pad, int k_pad, int N, int d, int relu, int pool, void* stream,
+                      long long* trace, int trace_tiles) {
     CNA_CHECK(x && wv_packed && wh_packed && y, "null pointer");
     CNA_CHECK(B > 0, "bad batch");
     CNA_CHECK(shape_ok(H, W, c_pad, k_pad, N, d), "configuration not supported by the fused kernel "
@@ -515,7 +578,8 @@ int cna_lowrank2_fused_forward(const void* x, const void* wv_packed, const void*
     }
     const int CK = pick_ck(c_pad);
     LR2Params p{};
-    p.B = B; p.H = H; p.W = W; p.N = N; p.relu = relu;
+    CNA_CHECK(!pool || (H % 2 == 0 && W % 2 == 0), "fused 2x2 max-pool needs even H and W");
+    p.B = B; p.H = H; p.W = W; p.N = N; p.relu = relu; p.pool = pool ? 1 : 0; p.trace = trace; p.trace_tiles = trace_tiles;
     p.nch = c_pad / CK; p.nnt = N / kNT;
     p.tiles_w = ceil_div(W, kValidCols); p.tiles_h = ceil_div(H, kTileRows);
     long long ntiles = (long long)B * p.tiles_w * p.tiles_h;
@@ -544,9 +608,10 @@ int cna_lowrank2_fused_forward(const void* x, const void* wv_packed, const void*
         if (encode(&tm_wh, wh_packed, 2, dims, str, box, swizzle_for(k_pad * 2))) return 1;
     }
     {
-        cuuint64_t dims[4] = {(cuuint64_t)N, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-        cuuint64_t str[3] = {(cuuint64_t)N * 2, (cuuint64_t)W * N * 2, (cuuint64_t)H * W * N * 2};
-        cuuint32_t box[4] = {kNT, kValidCols, kTileRows, 1};
+        const int Wy = pool ? W / 2 : W, Hy = pool ? H / 2 : H;
+        cuuint64_t dims[4] = {(cuuint64_t)N, (cuuint64_t)Wy, (cuuint64_t)Hy, (cuuint64_t)B};
+        cuuint64_t str[3] = {(cuuint64_t)N * 2, (cuuint64_t)Wy * N * 2, (cuuint64_t)Hy * Wy * N * 2};
+        cuuint32_t box[4] = {kNT, (cuuint32_t)(pool ? kValidCols / 2 : kValidCols), (cuuint32_t)(pool ? kTileRows / 2 : kTileRows), 1};
         if (encode(&tm_y, y, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     }
     int grid = std::min(p.ntiles, num_sms);
@@ -574,6 +639,17 @@ int cna_lowrank2_fused_forward(const void* x, const void* wv_packed, const void*
 #undef CNA_LR2_LAUNCH
     CNA_LAUNCH_OK();
     return 0;
+}
+
+int cna_lowrank2_fused_forward(const void* x, const void* wv_packed, const void* wh_packed, const float* bias, void* y,
+                               int B, int H, int W, int c_pad, int k_pad, int N, int d, int relu, int pool, void* stream) {
+    return lr2_launch(x, wv_packed, wh_packed, bias, y, B, H, W, c_pad, k_pad, N, d, relu, pool, stream, nullptr, 0);
+}
+
+int cna_lowrank2_fused_forward_traced(const void* x, const void* wv_packed, const void* wh_packed, const float* bias, void* y,
+                                      int B, int H, int W, int c_pad, int k_pad, int N, int d, int relu, void* stream,
+                                      long long* trace, int trace_tiles) {
+    return lr2_launch(x, wv_packed, wh_packed, bias, y, B, H, W, c_pad, k_pad, N, d, relu, 0, stream, trace, trace_tiles);
 }
 
 }  // extern "C"

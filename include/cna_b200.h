@@ -95,9 +95,16 @@ int cna_fix_padding_bias(void* x, const float* res, int B, int H, int W, int C, 
 int cna_lowrank2_pack(const float* v_w /*(K,C,d,1)*/, const float* h_w /*(N,K,1,d)*/,
                       void* wv_packed, void* wh_packed, int C, int K, int N, int d,
                       int c_pad, int k_pad, void* stream);
+/* relu: fuse max(.,0); pool: additionally fuse a 2x2/stride-2 max-pool (H, W even) — y is then [B, H/2, W/2, N]. */
 int cna_lowrank2_fused_forward(const void* x, const void* wv_packed, const void* wh_packed, const float* bias,
                                void* y, int B, int H, int W, int c_pad, int k_pad, int N, int d,
-                               int relu, void* stream);
+                               int relu, int pool, void* stream);
+/* Diagnostic variant: CTA 0 additionally records clock64() stamps, 10 per tile for its first `trace_tiles` tiles
+ * (0 x issued, 1 GEMM1 turn, 2 x landed, 3 GEMM1 issued, 4 GEMM2 turn, 5 T ready, 6 T-epilogue start, 7 T stored,
+ * 8 Y-epilogue start, 9 y store issued).  Used by benchmarks/trace_lowrank2.py to read the pipeline's critical path. */
+int cna_lowrank2_fused_forward_traced(const void* x, const void* wv_packed, const void* wh_packed, const float* bias,
+                                      void* y, int B, int H, int W, int c_pad, int k_pad, int N, int d, int relu,
+                                      void* stream, long long* trace, int trace_tiles);
 /* 1 if the fused kernel supports this configuration, else 0 (caller falls back to two cna_conv_taps_forward). */
 int cna_lowrank2_fused_supported(int H, int W, int c_pad, int k_pad, int N, int d);
 

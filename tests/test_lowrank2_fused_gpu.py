@@ -84,3 +84,47 @@ def test_linearity_at_full_size():
     t = B.conv_taps(x[:2].contiguous(), wv_g, None, K, 3, 0, (1, 1), 1)
     yg = B.conv_taps(t, wh_g, None, N, 3, 1, (1, 1), 1)
     assert O.compare4d(yg.permute(0, 3, 1, 2).float().cpu(), y1[:2].permute(0, 3, 1, 2).float().cpu()) < 1e-3
+
+
+@pytest.mark.parametrize("case", [(2, 64, 28, 28, 32, 64), (1, 128, 14, 42, 64, 128), (2, 16, 16, 20, 16, 64)])
+def test_fused_relu_maxpool_epilogue(case):
+    """ReLU + 2x2 max-pool fused into the epilogue == max_pool2d(relu(layer(x))) of the bf16 oracle (max is exact)."""
+    import torch.nn.functional as F
+    from approx import backend as B
+    Bn, C, H, W, K, N = case
+    v_w, h_w, b = make(C, K, N, 21)
+    x = torch.randn(Bn, C, H, W, generator=torch.Generator().manual_seed(9)).bfloat16()
+    ref = F.max_pool2d(torch.relu(O.lowrank2_forward(x, v_w, h_w, b, (1, 1), (1, 1))).float(), 2)
+    wv, wh = B.lowrank2_pack(v_w.cuda().float(), h_w.cuda().float())
+    xn = B.to_nhwc(x.cuda(), B.round_up(C, 16))
+    y = B.lowrank2_fused(xn, wv, wh, b.float().cuda(), relu=True, pool=True)
+    assert y.shape == (Bn, H // 2, W // 2, N)
+    got = y.permute(0, 3, 1, 2).float().cpu()
+    assert O.compare4d(ref, got) < 1e-3
+    full = B.lowrank2_fused(xn, wv, wh, b.float().cuda(), relu=True)
+    assert torch.equal(B.maxpool2x2(full), y)          # bit-identical to pooling the un-fused output
+
+
+def test_vgg_trunk_matches_oracle_small():
+    """13-layer trunk (rank 16) on a 2 x 3 x 32 x 32 input against the oracle run in bf16."""
+    import torch.nn.functional as F
+    from approx.models import VGG16Scheme2Trunk, VGG16_CFG
+    torch.manual_seed(0)
+    trunk = VGG16Scheme2Trunk(16).bfloat16()
+    with torch.no_grad():
+        for m in trunk.conv_layers():
+            m.v_conv.weight.normal_(0, (1.0 / (3 * m.in_channels)) ** 0.5)
+            m.h_conv.weight.normal_(0, (2.0 / (3 * 16)) ** 0.5)
+    x = torch.randn(2, 3, 32, 32).bfloat16()
+    ref = x
+    it = iter(trunk.conv_layers())
+    for c in VGG16_CFG:
+        if c == "M":
+            ref = F.max_pool2d(ref.float(), 2).bfloat16()
+        else:
+            m = next(it)
+            ref = torch.relu(O.lowrank2_forward(ref, m.v_conv.weight.detach(), m.h_conv.weight.detach(),
+                                                m.h_conv.bias.detach(), (1, 1), (1, 1)))
+    y = trunk.cuda()(x.cuda())
+    assert y.shape == ref.shape == (2, 512, 1, 1)
+    assert O.compare4d(ref.float(), y.float().cpu()) < 2e-2      # 13 chained bf16 layers: rounding differences compound

@@ -52,48 +52,55 @@ def algorithmic_flops_per_image(K):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock, power and throttle reasons through NVML every few ms while the timed region runs
+    (the timed region is tens of ms, far below nvidia-smi's own sampling period)."""
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, period_s=0.002):
+        self.index, self.period, self.rows, self.stop_evt, self.t, self.err = index, period_s, [], threading.Event(), None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.index
+            if visible:
+                ids = [v.strip() for v in visible.split(",") if v.strip()]
+                if self.index < len(ids) and ids[self.index].isdigit():
+                    phys = int(ids[self.index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+            self.mx = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:  # noqa: BLE001
+            self.err = f"nvml unavailable: {e}"
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_evt.is_set():
+            try:
+                self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0,
+                                  nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)))
+            except Exception as e:  # noqa: BLE001
+                self.err = str(e)
+                return
+            time.sleep(self.period)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx = float(r[1])
-                for n, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except Exception:
-                continue
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        if self.t is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "not started"], "samples": 0}
+        self.stop_evt.set()
+        self.t.join(timeout=2)
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap,
+                 "hw_power_brake": nv.nvmlClocksEventReasonHwPowerBrakeSlowdown}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = sorted(n for n, bit in names.items() if any(r[2] & bit for r in self.rows))
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx, "reasons": reasons,
+                "power_w_max": max((r[1] for r in self.rows), default=None), "samples": len(sm)}
 
 
 def cpu_reference_run(rank_k, sample_batch, iters, warmup, threads=None):
@@ -215,18 +222,24 @@ def run_ours(args):
         conv_ms = sum(a.elapsed_time(b) for row in ev for (a, b) in row)
         clocks = sampler.stop() if rank == 0 else None
 
-        # ---- end to end through the public module API with host buffers ----
-        def e2e_step():
-            xd = x_host.to(dev, non_blocking=True)
-            out = trunk(xd)
-            y_host.copy_(out, non_blocking=True)
+        # ---- end to end through the public API with HOST buffers: every step copies its (pinned) NCHW bf16 images
+        # to the device, runs the trunk module (layout conversion included) and reads the result back to the host.
+        # approx.pipeline.HostPipeline overlaps the copies of neighbouring steps with the kernels (3 streams).
+        from approx.pipeline import HostPipeline
+        pipe = HostPipeline(trunk, dev, depth=2)
         for _ in range(min(args.warmup, 3)):
-            e2e_step()
+            pipe.submit(x_host, y_host)
+        pipe.wait()
         sync_all()
+        cur = torch.cuda.current_stream()
         e_beg, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e_beg.record()
+        for st in (pipe.s_in, pipe.s_run, pipe.s_out):
+            st.wait_event(e_beg)
         for _ in range(args.steps):
-            e2e_step()
+            pipe.submit(x_host, y_host)
+        for st in (pipe.s_in, pipe.s_run, pipe.s_out):
+            cur.wait_stream(st)
         e_end.record()
         sync_all()
         e2e_ms = e_beg.elapsed_time(e_end)

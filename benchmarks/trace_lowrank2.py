@@ -19,7 +19,7 @@ EV = ["x_issued", "g1_turn", "x_landed", "g1_issued", "g2_turn", "t_ready", "tep
 
 def main():
     ap = argparse.ArgumentParser()
-    for k, v in dict(C=64, N=64, K=64, H=224, batch=64, tiles=48).items():
+    for k, v in dict(C=64, N=64, K=64, H=224, batch=64, tiles=48, quiet=0).items():
         ap.add_argument(f"--{k}", type=int, default=v)
     a = ap.parse_args()
     from approx import backend as B
@@ -32,10 +32,16 @@ def main():
         y, tr = B.lowrank2_fused_traced(x, wv, wh, None, a.tiles)
     torch.cuda.synchronize()
     t = tr.cpu().numpy().astype("int64")
+    wall = t[a.tiles]
+    t = t[:a.tiles]
+    cyc, ns = wall[2] - wall[0], wall[3] - wall[1]
+    ntile = a.batch * -(-a.H // 8) * -(-a.H // 14)
+    print(f"CTA 0: {cyc} cycles in {ns} ns -> effective SM clock {cyc / ns * 1e3:.0f} MHz; {ntile} tiles, "
+          f"{-(-ntile // 148)} per CTA -> {cyc / -(-ntile // 148):.0f} cycles/tile incl. prologue")
     t0 = t[t > 0].min()
     t = t - t0
     print("tile " + " ".join(f"{e:>10s}" for e in EV))
-    for i in range(a.tiles):
+    for i in range(0 if not a.quiet else a.tiles, a.tiles):
         print(f"{i:4d} " + " ".join(f"{v:10d}" for v in t[i]))
     import numpy as np
     lo = a.tiles // 3

@@ -191,9 +191,11 @@ class LowRankExpConvV2(nn.Module):
 
     def forward(self, x):
         _ops.check_input(x)
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            if not self._trainable_here():
-                raise NotImplementedError("backward kernels cover the dense scheme-2 layer with stride 1 and 'same' padding")
+        # Backward kernels cover the dense scheme-2 layer with stride 1 and 'same' padding.  Every other form runs
+        # forward-only like the rest of this backend's layers: its output carries no grad_fn, so a `backward()`
+        # through it fails in autograd instead of silently training nothing.
+        if (torch.is_grad_enabled() and self._trainable_here()
+                and (x.requires_grad or any(p.requires_grad for p in self.parameters()))):
             return _Scheme2Function.apply(x, self.v_conv.weight, self.h_conv.weight, self.h_conv.bias, self)
         H, W = x.shape[2:]
         c_pad = B.round_up(self.in_channels, 16) if self._fusable(x.dtype, H, W) else None

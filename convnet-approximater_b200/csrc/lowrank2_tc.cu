@@ -162,6 +162,16 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     const uint32_t tmem_T = tmem;            // + buf*64
     const uint32_t tmem_Y = tmem + 128;      // + buf*64
 
+    // diagnostic: row `trace_tiles` of the trace holds {clock64, globaltimer} at CTA 0's start and end (effective SM clock)
+    auto stamp_wall = [&](int slot) {
+        if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+            unsigned long long gt;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+            p.trace[p.trace_tiles * kTraceEv + slot] = clock64();
+            p.trace[p.trace_tiles * kTraceEv + slot + 1] = (long long)gt;
+        }
+    };
+    stamp_wall(0);
     const int first = blockIdx.x, step = gridDim.x;
     const int my_tiles = first < p.ntiles ? (p.ntiles - first + step - 1) / step : 0;
     auto stamp = [&](int it, int ev) {
@@ -433,6 +443,7 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     // ---------------- teardown ----------------
     tc_fence_before_sync();
     __syncthreads();
+    stamp_wall(2);
     if (warp == 1) {
         __syncwarp();
         tmem_dealloc<kTmemCols>(tmem);

@@ -41,6 +41,7 @@ struct P {
     int groups;    // groups of 12 UMMAs (3 taps x 4 k-steps), one commit per group
     int sts_kb;    // KB of st.shared.v4 traffic per group issued by 4 other warps (0 = none)
     int ldtm;      // 1: 4 other warps run tcgen05.ld loops concurrently
+    int rot;       // >1: rotate the accumulator per INSTRUCTION over `rot` independent 64-column accumulators (N=64 only)
     long long* out;
 };
 
@@ -80,8 +81,10 @@ __global__ void __launch_bounds__(288, 1) umma_rate(P p) {
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
                         const uint64_t b = bdesc + ((tap * 0 + kk * 32) >> 4);
-                        if (p.mode == 3) umma_ts(d, tmem + 384 + tap * 32 + kk * 8, b, idesc, (uint32_t)((tap | kk) != 0));
-                        else umma_bf16(d, adesc + ((tap * tap_step + kk * kk_step) >> 4), b, idesc, (uint32_t)((tap | kk) != 0));
+                        const uint32_t dd = p.rot > 1 ? tmem + ((tap * 4 + kk) % p.rot) * 64 : d;
+                        const uint32_t accf = p.rot > 1 ? (uint32_t)(g != 0) : (uint32_t)((tap | kk) != 0);
+                        if (p.mode == 3) umma_ts(dd, tmem + 384 + tap * 32 + kk * 8, b, idesc, accf);
+                        else umma_bf16(dd, adesc + ((tap * tap_step + kk * kk_step) >> 4), b, idesc, accf);
                     }
             }
             umma_commit(bar);
@@ -271,6 +274,54 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma2_rate(i
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
 }
 
+// W issuing warps, each with its own accumulator chain (groups of 12 into one 64/128/256-column accumulator)
+__global__ void __launch_bounds__(128, 1) umma_multi_issuer(int W, int N, int mode, int groups, long long* out) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    __shared__ uint64_t bar_store[4];
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bar_store[i]), 1); fence_mbar_init(); }
+    for (uint32_t i = threadIdx.x; i < (128u * 1024u) / 16u; i += blockDim.x)
+        asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(base + i * 16u), "r"(0u) : "memory");
+    if (warp == 0) tmem_alloc<512>(smem_u32(&tmem_slot));
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    __syncthreads();
+    const long long t0 = clock64();
+    if (warp < W) {
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
+        const uint64_t bdesc = desc_hi(16, 8 * 128, 2) + ((base + 48 * 1024) >> 4);
+        const uint64_t adesc = desc_hi(16, 8 * 128, 2) + ((base + warp * 2048) >> 4);
+        const uint32_t d = tmem + warp * (N <= 128 ? N : 0);
+        const uint32_t bar = smem_u32(&bar_store[warp]);
+        if (elect_one()) {
+            for (int g = 0; g < groups; ++g) {
+#pragma unroll
+                for (int tap = 0; tap < 3; ++tap)
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        if (mode == 3) umma_ts(d, tmem + 384 + tap * 32 + kk * 8, bdesc + ((kk * 32) >> 4), idesc, (uint32_t)((tap | kk) != 0));
+                        else umma_bf16(d, adesc + ((tap * 16 * 128 + kk * 32) >> 4), bdesc + ((kk * 32) >> 4), idesc, (uint32_t)((tap | kk) != 0));
+                    }
+            }
+            umma_commit(bar);
+        }
+        __syncwarp();
+        mbar_wait(bar, 0);
+    }
+    __syncthreads();
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) out[0] = t1 - t0;
+    (void)lane;
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
 int main() {
     long long* out;
     CK(cudaMallocManaged(&out, 64 * sizeof(long long)));
@@ -281,7 +332,7 @@ int main() {
     for (int mode = 0; mode < 4; ++mode)
         for (int ni = 0; ni < 3; ++ni)
             for (int noise = 0; noise < 3; ++noise) {
-                P p{mode, Ns[ni], 400, noise == 1 ? 1000 : 0, noise == 2 ? 1 : 0, out};
+                P p{mode, Ns[ni], 400, noise == 1 ? 1000 : 0, noise == 2 ? 1 : 0, 1, out};
                 for (int i = 0; i < 16; ++i) out[i] = 0;
                 umma_rate<<<1, 288, 200 * 1024>>>(p);
                 CK(cudaDeviceSynchronize());
@@ -292,6 +343,25 @@ int main() {
                 if (noise == 1) { double kb = out[2] + out[3] + out[4] + out[5]; printf("  STS %.1f B/cyc", kb * 1024.0 / out[0]); }
                 if (noise == 2) { double n = out[6] + out[7] + out[8] + out[9]; printf("  LDTM %.1f B/cyc", n * 32 * 64 * 4 / out[0]); }
                 printf("\n");
+            }
+    printf("== independent accumulators rotated per instruction (N=64) ==\n");
+    for (int mode = 0; mode < 4; mode += 3)
+        for (int rot = 1; rot <= 4; rot *= 2) {
+            P p{mode, 64, 400, 0, 0, rot, out};
+            umma_rate<<<1, 288, 200 * 1024>>>(p);
+            CK(cudaDeviceSynchronize());
+            printf("%-32s N= 64 rot %d : %7.1f cyc/UMMA\n", mname[mode], rot, (double)out[0] / (p.groups * 12.0));
+        }
+    printf("== several issuing warps, one accumulator chain each ==\n");
+    CK(cudaFuncSetAttribute(umma_multi_issuer, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    for (int mode = 0; mode < 4; mode += 3)
+        for (int N = 64; N <= 128; N *= 2)
+            for (int W = 1; W <= 4; ++W) {
+                if (N == 128 && W > 2 && mode == 3) continue;
+                umma_multi_issuer<<<1, 128, 200 * 1024>>>(W, N, mode, 400, out);
+                CK(cudaDeviceSynchronize());
+                printf("%-24s N=%3d  %d issuing warps: %7.1f cyc per UMMA overall (%5.1f%% of tensor peak)\n", mname[mode], N, W,
+                       (double)out[0] / (400 * 12.0 * W), 100.0 * (128.0 * N / 256.0) * 400 * 12 * W / out[0]);
             }
     printf("== TMEM drain: tcgen05.ld 32x32b.x16 + wait per 16 columns ==\n");
     for (int warps = 4; warps <= 16; warps *= 2) {

@@ -30,6 +30,7 @@
 #include "ptx.cuh"
 
 #include <cuda.h>
+#include <stdlib.h>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -37,7 +38,7 @@
 namespace cna {
 using namespace ptx;
 
-constexpr int kThreads = 352;        // warp 0 TMA, warp 1 GEMM1 issuer, warps 2-5 T-epilogue, 6-9 Y-epilogue, warp 10 GEMM2 issuer
+constexpr int kThreads = 480;        // warp 0 TMA, 1 GEMM1 issuer, 2-5 T-epilogue, 6-9 Y-epilogue group 0, 10 GEMM2 issuer, 11-14 Y-epilogue group 1
 constexpr int kTileRows = 8;           // output rows per tile
 constexpr int kTileCols = 16;          // computed columns per tile (14 valid + 2 halo)
 constexpr int kValidCols = kTileCols - 2;
@@ -72,8 +73,9 @@ struct LR2Params {
     uint32_t off_y, y_buf;        // y staging (2)
     uint32_t off_p;               // pooled staging (2 x 4 KB), only when pool
     uint32_t off_bias, off_bar;
+    int debug;             // diagnostic bit mask (CNA_LR2_DEBUG): see lr2_launch; 0 in production
     long long* trace;      // diagnostic: per-tile clock64() stamps of CTA 0 (NULL = off), kTraceEv slots per tile
-    int trace_tiles;
+    int trace_tiles, trace_skip;
 };
 
 __host__ __device__ constexpr uint32_t swz_type(int row_bytes) { return row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u); }
@@ -175,7 +177,8 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     const int first = blockIdx.x, step = gridDim.x;
     const int my_tiles = first < p.ntiles ? (p.ntiles - first + step - 1) / step : 0;
     auto stamp = [&](int it, int ev) {
-        if (p.trace != nullptr && blockIdx.x == 0 && it < p.trace_tiles) p.trace[it * kTraceEv + ev] = clock64();
+        if (p.trace != nullptr && blockIdx.x == 0 && it >= p.trace_skip && it < p.trace_skip + p.trace_tiles)
+            p.trace[(it - p.trace_skip) * kTraceEv + ev] = clock64();
     };
 
     if (warp == 0) {
@@ -199,6 +202,7 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             auto load_x = [&](int it) {
                 TileCoord t = decode_tile(first + it * step, p);
                 for (int ch = 0; ch < p.nch; ++ch) {
+                    if ((p.debug & 16) && it * p.nch + ch >= p.stages) continue;
                     mbar_wait(bar(BAR_XEMPTY + xs), xph ^ 1u);
                     if (elect_one()) {
                         mbar_arrive_expect_tx(bar(BAR_XFULL + xs), x_bytes + (p.resident ? 0u : v_bytes));
@@ -249,7 +253,7 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 tc_fence_after_sync();
                 const uint32_t d = tmem_T + buf * 64;
                 for (int ch = 0; ch < p.nch; ++ch) {
-                    mbar_wait(bar(BAR_XFULL + xs), xph);
+                    if (!((p.debug & 16) && it * p.nch + ch >= p.stages)) mbar_wait(bar(BAR_XFULL + xs), xph);
                     tc_fence_after_sync();
                     if (lane == 0 && ch == 0) stamp(it, 2);
                     const uint64_t a0 = xdesc + ((base + p.off_x + xs * p.x_stage) >> 4);
@@ -261,7 +265,7 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                             for (int kk = 0; kk < CK / 16; ++kk)
                                 umma_bf16(d, a0 + ((dy * kTileCols * XROW + kk * 32) >> 4), b0 + ((dy * KP * XROW + kk * 32) >> 4),
                                           idesc1, (uint32_t)((ch | dy | kk) != 0));
-                        umma_commit(bar(BAR_XEMPTY + xs));
+                        if (!(p.debug & 16)) umma_commit(bar(BAR_XEMPTY + xs));
                         if (ch == p.nch - 1) umma_commit(bar(BAR_TACC_FULL + buf));
                     }
                     __syncwarp();
@@ -336,6 +340,7 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             mbar_arrive(bar(BAR_TACC_EMPTY + buf));          // accumulator drained: GEMM1 of tile it+2 may start
             mbar_wait(bar(BAR_TSM_EMPTY + buf), ph ^ 1u);     // GEMM2 of tile it-2 has finished reading this T buffer
             const uint32_t tb = base + p.off_t + buf * p.t_buf + slot_off;
+            if (!(p.debug & 4))
 #pragma unroll
             for (int ch = 0; ch < TCH; ++ch)
                 st_shared_v4(tb + ch * kTLbo,
@@ -343,99 +348,112 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                              pack_bf16(__uint_as_float(v[ch * 8 + 2]), __uint_as_float(v[ch * 8 + 3])),
                              pack_bf16(__uint_as_float(v[ch * 8 + 4]), __uint_as_float(v[ch * 8 + 5])),
                              pack_bf16(__uint_as_float(v[ch * 8 + 6]), __uint_as_float(v[ch * 8 + 7])));
-            fence_proxy_async_smem();
+            if (!(p.debug & 8)) fence_proxy_async_smem();
             mbar_arrive(bar(BAR_TSM_FULL + buf));
             if (threadIdx.x == 64) stamp(it, 7);
         }
-    } else if (warp < 10) {
-        // =========================== Y-epilogue warps (6..9) ===========================
-        // TMEM accumulator of GEMM2 -> +bias, ReLU -> bf16 -> swizzled staging -> TMA store.
+    } else if (warp < 10 || warp >= 11) {
+        // =========================== Y-epilogue warps: group 0 = warps 6..9, group 1 = warps 11..14 ===========================
+        // TMEM accumulator of GEMM2 -> +bias, ReLU -> bf16 -> swizzled staging -> TMA store.  Group g owns Y accumulator g,
+        // staging buffer g and every N-tile q with (q & 1) == g, so two N-tiles are in the epilogue at any time: one
+        // group's ld -> math -> st -> fence -> store chain (~1300 cycles) would otherwise bound the whole pipeline.
+        const int g = warp >= 11 ? 1 : 0;
         const int lg = warp & 3;
         const int m = lg * 32 + lane;            // accumulator row: m = yc*8 + r
         const uint32_t lane_addr = (uint32_t)(lg * 32) << 16;
-        const int et = (warp - 6) * 32 + lane;   // 0..127
+        const int et = (warp - (g ? 11 : 6)) * 32 + lane;   // 0..127 inside the group
+        const uint32_t bar_a = 1 + 3 * g, bar_b = 2 + 3 * g, bar_c = 3 + 3 * g;
         const int yc = m >> 3, r = m & 7;
         const bool valid = yc >= 1 && yc <= kValidCols;
-        const uint32_t srow = (uint32_t)(r * kValidCols + (yc - 1));      // staging row (TMA box order: row, col)
-        const uint32_t row_off = srow * 128u, sw = srow & 7u;             // 128B-swizzle: chunk ^= row & 7
+        // staging rows in TMA box order (col, row) — the y tensor map lists H before W — so the 8 lanes of a store
+        // phase hit 8 consecutive 128-byte rows: with the 128B swizzle (chunk ^= row & 7) that is conflict free.
+        const uint32_t srow = (uint32_t)((yc - 1) * kTileRows + r);
+        const uint32_t row_off = srow * 128u, sw = (uint32_t)r;
         const float lo = p.relu ? 0.f : -INFINITY;
-        int q = 0;
-        for (int j = 0; j < my_tiles; ++j) {
+        const uint32_t sb = base + p.off_y + g * p.y_buf;
+        const uint32_t pb = base + p.off_p + g * 4096;
+        const uint32_t tacc = tmem_Y + g * 64 + lane_addr;
+        const int nq = my_tiles * p.nnt;
+        int j = 0, nt = g;                       // q = j * nnt + nt
+        while (nt >= p.nnt) { nt -= p.nnt; ++j; }
+        for (int q = g; q < nq; q += 2) {
             TileCoord t = decode_tile(first + j * step, p);
-            for (int nt = 0; nt < p.nnt; ++nt, ++q) {
-                const int yb = q & 1;
-                const uint32_t sb = base + p.off_y + yb * p.y_buf;
-                mbar_wait(bar(BAR_YACC_FULL + yb), (uint32_t)((q >> 1) & 1));
-                tc_fence_after_sync();
-                if (et == 0 && nt == 0) stamp(j, 8);
-                uint32_t v[kNT];
+            mbar_wait(bar(BAR_YACC_FULL + g), (uint32_t)((q >> 1) & 1));
+            tc_fence_after_sync();
+            if (et == 0 && nt == 0) stamp(j, 8);
+            uint32_t v[kNT];
 #pragma unroll
-                for (int c16 = 0; c16 < kNT / 16; ++c16) tmem_ld16(tmem_Y + yb * 64 + lane_addr + c16 * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[c16 * 16]));
-                tmem_ld_wait();
-                tc_fence_before_sync();
-                mbar_arrive(bar(BAR_YACC_EMPTY + yb));       // accumulator drained: next N-tile's GEMM2 may start
-                // staging buffer yb was handed to a TMA store two N-tiles ago: wait until it has been read
-                if (et == 0) tma_store_wait_read<1>();
-                named_bar_sync(1, 128);
-                if (valid) {
-                    const float* bz = sbias + nt * kNT;
+            for (int c16 = 0; c16 < kNT / 16; ++c16) tmem_ld16(tacc + c16 * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[c16 * 16]));
+            tmem_ld_wait();
+            tc_fence_before_sync();
+            mbar_arrive(bar(BAR_YACC_EMPTY + g));        // accumulator drained: GEMM2 of N-tile q+2 may start
+            uint32_t w[kNT / 2];
+            {
+                const float* bz = sbias + nt * kNT;
 #pragma unroll
-                    for (int ch = 0; ch < kNT / 8; ++ch) {
-                        float4 b0 = ld_shared_f4(bz + ch * 8), b1 = ld_shared_f4(bz + ch * 8 + 4);
-                        uint32_t w0 = pack_bf16(fmaxf(__uint_as_float(v[ch * 8 + 0]) + b0.x, lo), fmaxf(__uint_as_float(v[ch * 8 + 1]) + b0.y, lo));
-                        uint32_t w1 = pack_bf16(fmaxf(__uint_as_float(v[ch * 8 + 2]) + b0.z, lo), fmaxf(__uint_as_float(v[ch * 8 + 3]) + b0.w, lo));
-                        uint32_t w2 = pack_bf16(fmaxf(__uint_as_float(v[ch * 8 + 4]) + b1.x, lo), fmaxf(__uint_as_float(v[ch * 8 + 5]) + b1.y, lo));
-                        uint32_t w3 = pack_bf16(fmaxf(__uint_as_float(v[ch * 8 + 6]) + b1.z, lo), fmaxf(__uint_as_float(v[ch * 8 + 7]) + b1.w, lo));
-                        st_shared_v4(sb + row_off + (((uint32_t)ch ^ sw) << 4), w0, w1, w2, w3);
-                    }
-                }
-                if (!p.pool) {
-                    fence_proxy_async_smem();
-                    named_bar_sync(2, 128);
-                    if (et == 0) {
-                        tma_store_4d(&tm_y, sb, nt * kNT, t.w0, t.h0, t.b);
-                        tma_store_commit();
-                        if (nt == p.nnt - 1) stamp(j, 9);
-                    }
-                } else {
-                    // 2x2 max-pool of the staged 8 x 14 tile -> 4 x 7 pooled tile (bf16 max commutes with the rounding)
-                    named_bar_sync(2, 128);
-                    const uint32_t pb = base + p.off_p + yb * 4096;
-#pragma unroll
-                    for (int rep = 0; rep < 2; ++rep) {
-                        const int id = et + rep * 128;            // 28 pooled pixels x 8 chunks of 16 bytes
-                        if (id < 28 * 8) {
-                            const int pp = id >> 3, ch = id & 7, pr = pp / 7, pc = pp - pr * 7;
-                            uint4 m4 = make_uint4(0, 0, 0, 0);
-#pragma unroll
-                            for (int a = 0; a < 2; ++a)
-#pragma unroll
-                                for (int bq = 0; bq < 2; ++bq) {
-                                    const uint32_t row = (uint32_t)((2 * pr + a) * kValidCols + 2 * pc + bq);
-                                    uint4 v4;
-                                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                                                 : "=r"(v4.x), "=r"(v4.y), "=r"(v4.z), "=r"(v4.w)
-                                                 : "r"(sb + row * 128u + (((uint32_t)ch ^ (row & 7u)) << 4)));
-                                    if (a == 0 && bq == 0) m4 = v4;
-                                    else {
-                                        __nv_bfloat162* mm = reinterpret_cast<__nv_bfloat162*>(&m4);
-                                        const __nv_bfloat162* vv = reinterpret_cast<const __nv_bfloat162*>(&v4);
-#pragma unroll
-                                        for (int e = 0; e < 4; ++e) mm[e] = __hmax2(mm[e], vv[e]);
-                                    }
-                                }
-                            st_shared_v4(pb + (uint32_t)pp * 128u + (((uint32_t)ch ^ ((uint32_t)pp & 7u)) << 4), m4.x, m4.y, m4.z, m4.w);
-                        }
-                    }
-                    fence_proxy_async_smem();
-                    named_bar_sync(3, 128);
-                    if (et == 0) {
-                        tma_store_4d(&tm_y, pb, nt * kNT, t.w0 >> 1, t.h0 >> 1, t.b);
-                        tma_store_commit();
-                        if (nt == p.nnt - 1) stamp(j, 9);
-                    }
+                for (int ch = 0; ch < kNT / 8; ++ch) {
+                    float4 b0 = ld_shared_f4(bz + ch * 8), b1 = ld_shared_f4(bz + ch * 8 + 4);
+                    w[ch * 4 + 0] = pack_bf16(fmaxf(__uint_as_float(v[ch * 8 + 0]) + b0.x, lo), fmaxf(__uint_as_float(v[ch * 8 + 1]) + b0.y, lo));
+                    w[ch * 4 + 1] = pack_bf16(fmaxf(__uint_as_float(v[ch * 8 + 2]) + b0.z, lo), fmaxf(__uint_as_float(v[ch * 8 + 3]) + b0.w, lo));
+                    w[ch * 4 + 2] = pack_bf16(fmaxf(__uint_as_float(v[ch * 8 + 4]) + b1.x, lo), fmaxf(__uint_as_float(v[ch * 8 + 5]) + b1.y, lo));
+                    w[ch * 4 + 3] = pack_bf16(fmaxf(__uint_as_float(v[ch * 8 + 6]) + b1.z, lo), fmaxf(__uint_as_float(v[ch * 8 + 7]) + b1.w, lo));
                 }
             }
+            // this group's staging buffer was handed to a TMA store one item ago: wait until it has been read
+            if (et == 0) tma_store_wait_read<0>();
+            named_bar_sync(bar_a, 128);
+            if (valid && !(p.debug & 2)) {
+#pragma unroll
+                for (int ch = 0; ch < kNT / 8; ++ch)
+                    st_shared_v4(sb + row_off + (((uint32_t)ch ^ sw) << 4), w[ch * 4], w[ch * 4 + 1], w[ch * 4 + 2], w[ch * 4 + 3]);
+            }
+            if (!p.pool) {
+                if (!(p.debug & 8)) fence_proxy_async_smem();
+                named_bar_sync(bar_b, 128);
+                if (et == 0 && !(p.debug & 1)) {
+                    tma_store_4d(&tm_y, sb, nt * kNT, t.h0, t.w0, t.b);
+                    tma_store_commit();
+                    if (nt == p.nnt - 1) stamp(j, 9);
+                }
+            } else {
+                // 2x2 max-pool of the staged 8 x 14 tile -> 4 x 7 pooled tile (bf16 max commutes with the rounding)
+                named_bar_sync(bar_b, 128);
+#pragma unroll
+                for (int rep = 0; rep < 2; ++rep) {
+                    const int id = et + rep * 128;            // 28 pooled pixels x 8 chunks of 16 bytes
+                    if (id < 28 * 8) {
+                        const int pp = id >> 3, ch = id & 7, pc = pp >> 2, pr = pp & 3;     // pooled row index pp = pc*4 + pr
+                        uint4 m4 = make_uint4(0, 0, 0, 0);
+#pragma unroll
+                        for (int a = 0; a < 2; ++a)
+#pragma unroll
+                            for (int bq = 0; bq < 2; ++bq) {
+                                const uint32_t row = (uint32_t)((2 * pc + bq) * kTileRows + 2 * pr + a);
+                                uint4 v4;
+                                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                             : "=r"(v4.x), "=r"(v4.y), "=r"(v4.z), "=r"(v4.w)
+                                             : "r"(sb + row * 128u + (((uint32_t)ch ^ (row & 7u)) << 4)));
+                                if (a == 0 && bq == 0) m4 = v4;
+                                else {
+                                    __nv_bfloat162* mm = reinterpret_cast<__nv_bfloat162*>(&m4);
+                                    const __nv_bfloat162* vv = reinterpret_cast<const __nv_bfloat162*>(&v4);
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) mm[e] = __hmax2(mm[e], vv[e]);
+                                }
+                            }
+                        st_shared_v4(pb + (uint32_t)pp * 128u + (((uint32_t)ch ^ ((uint32_t)pp & 7u)) << 4), m4.x, m4.y, m4.z, m4.w);
+                    }
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(bar_c, 128);
+                if (et == 0 && !(p.debug & 1)) {
+                    tma_store_4d(&tm_y, pb, nt * kNT, t.h0 >> 1, t.w0 >> 1, t.b);
+                    tma_store_commit();
+                    if (nt == p.nnt - 1) stamp(j, 9);
+                }
+            }
+            nt += 2;
+            while (nt >= p.nnt) { nt -= p.nnt; ++j; }
         }
         if (et == 0) tma_store_wait_all<0>();
     }
@@ -591,6 +609,8 @@ static int lr2_launch(const void* x, const void* wv_packed, const void* wh_packe
     LR2Params p{};
     CNA_CHECK(!pool || (H % 2 == 0 && W % 2 == 0), "fused 2x2 max-pool needs even H and W");
     p.B = B; p.H = H; p.W = W; p.N = N; p.relu = relu; p.pool = pool ? 1 : 0; p.trace = trace; p.trace_tiles = trace_tiles;
+    { const char* dbg = getenv("CNA_LR2_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
+    { const char* sk = getenv("CNA_LR2_TRACE_SKIP"); p.trace_skip = sk ? atoi(sk) : 0; }
     p.nch = c_pad / CK; p.nnt = N / kNT;
     p.tiles_w = ceil_div(W, kValidCols); p.tiles_h = ceil_div(H, kTileRows);
     long long ntiles = (long long)B * p.tiles_w * p.tiles_h;
@@ -620,9 +640,11 @@ static int lr2_launch(const void* x, const void* wv_packed, const void* wh_packe
     }
     {
         const int Wy = pool ? W / 2 : W, Hy = pool ? H / 2 : H;
-        cuuint64_t dims[4] = {(cuuint64_t)N, (cuuint64_t)Wy, (cuuint64_t)Hy, (cuuint64_t)B};
-        cuuint64_t str[3] = {(cuuint64_t)N * 2, (cuuint64_t)Wy * N * 2, (cuuint64_t)Hy * Wy * N * 2};
-        cuuint32_t box[4] = {kNT, (cuuint32_t)(pool ? kValidCols / 2 : kValidCols), (cuuint32_t)(pool ? kTileRows / 2 : kTileRows), 1};
+        // dimension order (C, H, W, B): the staged tile is then (col, row)-major, which is what the epilogue's TMEM lane
+        // order (m = col*8 + row) writes without bank conflicts
+        cuuint64_t dims[4] = {(cuuint64_t)N, (cuuint64_t)Hy, (cuuint64_t)Wy, (cuuint64_t)B};
+        cuuint64_t str[3] = {(cuuint64_t)Wy * N * 2, (cuuint64_t)N * 2, (cuuint64_t)Hy * Wy * N * 2};
+        cuuint32_t box[4] = {kNT, (cuuint32_t)(pool ? kTileRows / 2 : kTileRows), (cuuint32_t)(pool ? kValidCols / 2 : kValidCols), 1};
         if (encode(&tm_y, y, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     }
     int grid = std::min(p.ntiles, num_sms);

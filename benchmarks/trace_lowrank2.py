@@ -14,7 +14,8 @@ for _p in (ROOT, os.path.join(ROOT, "convnet-approximater_b200")):
         sys.path.insert(0, _p)
 import torch  # noqa: E402
 
-EV = ["x_issued", "g1_turn", "x_landed", "g1_issued", "g2_turn", "t_ready", "tepi_start", "t_stored", "yepi_start", "y_store"]
+EV = ["x_issued", "g1_turn", "x_landed", "g1_issued", "g2_turn", "t_ready", "tepi_start", "t_stored", "yepi_start", "y_store",
+      "t_loaded", "a_free", "a_issued", "y_loaded", "stg_free", "y_staged", "g2_acc", "g2_issued", "y_sts_done", "y_fenced"]
 
 
 def main():
@@ -57,6 +58,14 @@ def main():
     print("  g2: turn -> T ready         ", (d[:, 5] - d[:, 4]).mean().round())
     print("  g2 ready -> yepi start      ", (d[:, 8] - d[:, 5]).mean().round(), "(GEMM2 execution + commit latency)")
     print("  yepi start -> store issued  ", (d[:, 9] - d[:, 8]).mean().round())
+    print("  T-epilogue: start -> TMEM loaded -> A buffer free -> copies issued -> stored:",
+          (d[:, 10] - d[:, 6]).mean().round(), (d[:, 11] - d[:, 10]).mean().round(), (d[:, 12] - d[:, 11]).mean().round(), (d[:, 7] - d[:, 12]).mean().round())
+    print("  GEMM2 warp: T ready -> accumulator free -> issued (-> next turn):", (d[:, 16] - d[:, 5]).mean().round(), (d[:, 17] - d[:, 16]).mean().round(),
+          (d[1:, 4] - d[:-1, 17]).mean().round())
+    print("  Y-epilogue thread 0: staging free -> its stores issued -> fence done -> group barrier:", (d[:, 18] - d[:, 14]).mean().round(),
+          (d[:, 19] - d[:, 18]).mean().round(), (d[:, 15] - d[:, 19]).mean().round())
+    print("  Y-epilogue: start -> TMEM loaded -> staging free -> staged -> store issued:",
+          (d[:, 13] - d[:, 8]).mean().round(), (d[:, 14] - d[:, 13]).mean().round(), (d[:, 15] - d[:, 14]).mean().round(), (d[:, 9] - d[:, 15]).mean().round())
 
 
 if __name__ == "__main__":

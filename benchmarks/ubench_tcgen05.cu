@@ -33,7 +33,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
         "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
         : "memory");
 }
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 struct P {
     int mode;      // A operand: 0 smem 128B-swizzle K-major (x tile), 1 smem no-swizzle pitch 144 (T tile), 2 no-swizzle pitch 128, 3 TMEM
@@ -322,6 +321,55 @@ __global__ void __launch_bounds__(128, 1) umma_multi_issuer(int W, int N, int mo
     if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
+// TMEM store shapes: 4 warps each writing 96 columns per iteration (the three bf16 copies of T) with x8 / x16 / x32 / x64 stores
+template <int X>
+__device__ __forceinline__ void tmem_stX(uint32_t taddr, const uint32_t* v) {
+    if constexpr (X == 8) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+                     "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+    } else if constexpr (X == 16) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr), "r"(v[0]),
+                     "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+                     "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+    } else {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+                     "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+                     "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),
+                     "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory");
+    }
+}
+template <int X>
+__global__ void __launch_bounds__(256, 1) tmem_st_shapes(int warps, int iters, long long* out) {
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) tmem_alloc<512>(smem_u32(&tmem_slot));
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    uint32_t v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = threadIdx.x + i;
+    __syncthreads();
+    long long t0 = clock64();
+    if (warp < warps) {
+        const uint32_t cbase = (uint32_t)(warp >> 2) * 96;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int c = 0; c < 96; c += X) tmem_stX<X>(tmem + lane_addr + cbase + c, v);
+            tmem_st_wait();
+            v[it & 31] += it;
+        }
+    }
+    __syncthreads();
+    long long t1 = clock64();
+    if (threadIdx.x == 0) out[0] = t1 - t0;
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
 int main() {
     long long* out;
     CK(cudaMallocManaged(&out, 64 * sizeof(long long)));
@@ -363,6 +411,15 @@ int main() {
                 printf("%-24s N=%3d  %d issuing warps: %7.1f cyc per UMMA overall (%5.1f%% of tensor peak)\n", mname[mode], N, W,
                        (double)out[0] / (400 * 12.0 * W), 100.0 * (128.0 * N / 256.0) * 400 * 12 * W / out[0]);
             }
+    printf("== TMEM store shapes, 96 columns per warp per iteration ==\n");
+    for (int warps = 4; warps <= 8; warps *= 2) {
+        tmem_st_shapes<8><<<1, 256>>>(warps, 2000, out); CK(cudaDeviceSynchronize());
+        printf("st x8  %d warps: %.1f cyc/iter (%.1f B/cyc/SM)\n", warps, out[0] / 2000.0, warps * 32 * 96 * 4 * 2000.0 / out[0]);
+        tmem_st_shapes<16><<<1, 256>>>(warps, 2000, out); CK(cudaDeviceSynchronize());
+        printf("st x16 %d warps: %.1f cyc/iter (%.1f B/cyc/SM)\n", warps, out[0] / 2000.0, warps * 32 * 96 * 4 * 2000.0 / out[0]);
+        tmem_st_shapes<32><<<1, 256>>>(warps, 2000, out); CK(cudaDeviceSynchronize());
+        printf("st x32 %d warps: %.1f cyc/iter (%.1f B/cyc/SM)\n", warps, out[0] / 2000.0, warps * 32 * 96 * 4 * 2000.0 / out[0]);
+    }
     printf("== TMEM drain: tcgen05.ld 32x32b.x16 + wait per 16 columns ==\n");
     for (int warps = 4; warps <= 16; warps *= 2) {
         tmem_rate<<<1, 512>>>(warps, 64, 2000, 0, out);

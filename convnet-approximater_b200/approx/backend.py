@@ -314,13 +314,13 @@ def lowrank2_pack(v_w, h_w):
 
 
 def lowrank2_fused_traced(x, wv, wh, bias, tiles=32, relu=False):
-    """Diagnostic: like lowrank2_fused, also returns a (tiles + 1, 10) int64 tensor of CTA-0 clock stamps."""
+    """Diagnostic: like lowrank2_fused, also returns a (tiles + 1, 20) int64 tensor of CTA-0 clock stamps."""
     _ready(x)
     Bn, H, W, cp = x.shape
     d, kp, _ = wv.shape
     N = wh.shape[1]
     y = torch.empty((Bn, H, W, N), device=x.device, dtype=torch.bfloat16)
-    trace = torch.zeros((tiles + 1, 10), device=x.device, dtype=torch.int64)   # last row: clock/globaltimer at start, end
+    trace = torch.zeros((tiles + 1, 20), device=x.device, dtype=torch.int64)   # last row: clock/globaltimer at start, end
     with torch.cuda.device(x.device):
         _check(lib().cna_lowrank2_fused_forward_traced(_p(x), _p(wv), _p(wh), _p(bias), _p(y), Bn, H, W, cp, kp, N, d,
                                                        int(relu), _stream(x), _p(trace), tiles))

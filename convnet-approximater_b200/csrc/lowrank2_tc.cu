@@ -24,11 +24,14 @@
 //     and N = 128 output channels per instruction when the layer has them.
 //   * y tile: TMEM -> registers (+bias, ReLU) -> swizzled smem staging [-> 2x2 max-pool] -> TMA store (clips at edges).
 //
-// Warp roles (512 threads, persistent CTAs, 1 per SM):
+// Warp roles (640 threads, persistent CTAs, 1 per SM):
 //   warp 0      x / Wv TMA producer          warp 15     Wh TMA producer (own ring, so neither ring blocks the other)
 //   warp 1      GEMM1 issuer                 warp 10     GEMM2 issuer   (two issuing warps: their waits overlap)
-//   warps 2-5   T-epilogue                   warps 6-9 / 11-14   Y-epilogue groups 0 / 1 (two N-tiles in flight)
-// TMEM (512 columns): T accumulators 2 x 64 | A copies 3 x KP/2 | Y accumulators 2 x NT2.
+//   warps 2-5 / 16-19   T-epilogue groups 0 / 1 (even / odd tiles)
+//   warps 6-9 / 11-14   Y-epilogue groups 0 / 1 (two 64-channel items in flight)
+// TMEM (512 columns): T accumulators 2 x 64 | A copies NABUF x 3 x KP/2 | Y accumulators 2 x NT2, with
+// NABUF = 2 for NT2 = 64 and 1 for NT2 = 128 (TMEM is full there; GEMM1 of the next tiles fills the tensor pipe
+// while the single A buffer is rewritten).
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -39,18 +42,17 @@
 namespace cna {
 using namespace ptx;
 
-constexpr int kThreads = 512;
+constexpr int kThreads = 640;
 constexpr int kTileRows = 8;           // output rows per tile
 constexpr int kTileCols = 16;          // computed columns per tile (14 valid + 2 halo)
 constexpr int kValidCols = kTileCols - 2;
 constexpr int kXRows = kTileRows + 2;  // x rows per tile (d = 3)
 constexpr int kNT = 64;                // output channels per Y-epilogue item / staging tile
 constexpr int kTmemCols = 512;
-constexpr uint32_t kTmemT = 0, kTmemA = 128, kTmemY = 256;
 constexpr int kMaxStages = 6;
 constexpr int kMaxHSlots = 12;         // Wh ring slots (one slot = one tap of one N-tile)
 constexpr int kMaxNTiles = 16;         // N <= 1024
-constexpr int kTraceEv = 10;
+constexpr int kTraceEv = 20;
 constexpr uint32_t kYBuf = kTileRows * kValidCols * 128;   // 14336-byte staging tile (112 pixels x 64 channels)
 
 struct LR2Params {
@@ -71,7 +73,7 @@ struct LR2Params {
     uint32_t off_y;               // y staging (2 x kYBuf, one per epilogue group)
     uint32_t off_p;               // pooled staging (2 x 4 KB), only when pool
     uint32_t off_bias, off_bar;
-    int debug;             // diagnostic bit mask (CNA_LR2_DEBUG): 1 skip y TMA store, 2 skip y staging stores, 16 load x only once
+    int debug;             // diagnostic bit mask (CNA_LR2_DEBUG): 1 skip y TMA store, 2 skip y staging stores, 16 load x only once, 32 skip A copies, 64 skip Y TMEM load, 128 skip GEMM1 MMAs
     long long* trace;      // diagnostic: per-tile clock64() stamps of CTA 0 (NULL = off), kTraceEv slots per tile
     int trace_tiles, trace_skip;
 };
@@ -84,7 +86,19 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// Same store without the compiler-level memory clobber: used where the only later readers are the async proxy / other
+// threads behind a fence + barrier (both volatile asm, so program order is kept) — lets the compiler hoist the bias
+// loads of the following chunks above the store instead of serialising load -> math -> store eight times.
+__device__ __forceinline__ void st_shared_v4_relaxed(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
+}
 __device__ __forceinline__ float4 ld_shared_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// volatile (keeps its place among the other volatile asm statements, i.e. stays where the software pipeline put it), no memory clobber
+__device__ __forceinline__ float4 ld_shared_f4_relaxed(uint32_t addr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+    return r;
+}
 
 // barrier indices (each 8 bytes) inside the barrier block
 enum : int {
@@ -95,9 +109,9 @@ enum : int {
     BAR_HEMPTY = BAR_HFULL + kMaxHSlots,   // [kMaxHSlots]
     BAR_TACC_FULL = BAR_HEMPTY + kMaxHSlots,   // [2] GEMM1 accumulator complete
     BAR_TACC_EMPTY = BAR_TACC_FULL + 2,    // [2] ... drained by the T-epilogue
-    BAR_TA_FULL = BAR_TACC_EMPTY + 2,      // bf16 copies of T written to TMEM
-    BAR_TA_EMPTY = BAR_TA_FULL + 1,        // GEMM2 of the tile has finished reading them
-    BAR_YACC_FULL = BAR_TA_EMPTY + 1,      // [2]
+    BAR_TA_FULL = BAR_TACC_EMPTY + 2,      // [2] bf16 copies of T written to TMEM
+    BAR_TA_EMPTY = BAR_TA_FULL + 2,        // [2] GEMM2 of the tile has finished reading them
+    BAR_YACC_FULL = BAR_TA_EMPTY + 2,      // [2]
     BAR_YACC_EMPTY = BAR_YACC_FULL + 2,    // [2]
     BAR_COUNT = BAR_YACC_EMPTY + 2
 };
@@ -124,6 +138,9 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     constexpr int XROW = CK * 2;            // bytes per x / Wv smem row (== swizzle span)
     constexpr int HROW = KP * 2;            // bytes per Wh smem row
     constexpr int ACOLS = KP / 2;           // TMEM columns of one bf16 copy of T
+    constexpr int NABUF = NT2 == 64 ? 2 : 1;   // buffers of bf16 T copies (TMEM is full at NT2 = 128)
+    constexpr uint32_t kTmemT = 0, kTmemA = 128, kTmemY = kTmemA + NABUF * 96;   // NT2=64: 0/128/320, NT2=128: 0/128/224
+    static_assert(kTmemY + 2 * NT2 <= 512, "TMEM budget");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -140,9 +157,8 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         for (int i = 0; i < kMaxStages; ++i) { mbar_init(bar(BAR_XFULL + i), 1); mbar_init(bar(BAR_XEMPTY + i), 1); }
         for (int i = 0; i < kMaxHSlots; ++i) { mbar_init(bar(BAR_HFULL + i), 1); mbar_init(bar(BAR_HEMPTY + i), 1); }
         mbar_init(bar(BAR_WFULL), 1);
-        mbar_init(bar(BAR_TA_FULL), 128);
-        mbar_init(bar(BAR_TA_EMPTY), 1);
         for (int i = 0; i < 2; ++i) {
+            mbar_init(bar(BAR_TA_FULL + i), 128);  mbar_init(bar(BAR_TA_EMPTY + i), 1);
             mbar_init(bar(BAR_TACC_FULL + i), 1);  mbar_init(bar(BAR_TACC_EMPTY + i), 128);
             mbar_init(bar(BAR_YACC_FULL + i), 1);  mbar_init(bar(BAR_YACC_EMPTY + i), NT2 == 64 ? 128 : 256);
         }
@@ -155,7 +171,7 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
     const uint32_t tmem_T = tmem + kTmemT;   // + buf*64
-    const uint32_t tmem_A = tmem + kTmemA;   // + dx*ACOLS
+    const uint32_t tmem_A = tmem + kTmemA;   // + abuf*96 + dx*ACOLS
     const uint32_t tmem_Y = tmem + kTmemY;   // + yb*NT2
 
     // diagnostic: row `trace_tiles` of the trace holds {clock64, globaltimer} at CTA 0's start and end (effective SM clock)
@@ -208,9 +224,9 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 if (lane == 0) stamp(it, 0);
             }
         }
-    } else if (warp == 15) {
+    } else if (warp == 15 && !p.resident) {
         // =========================== Wh TMA producer (streamed weights only) ===========================
-        if (my_tiles > 0 && !p.resident) {
+        if (my_tiles > 0) {
             constexpr uint32_t h_bytes = NT2 * HROW;
             int hs = 0; uint32_t hph = 0;
             for (int it = 0; it < my_tiles; ++it)
@@ -233,9 +249,14 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             int xs = 0; uint32_t xph = 0;
             if (p.resident) { mbar_wait(bar(BAR_WFULL), 0); tc_fence_after_sync(); }
             for (int it = 0; it < my_tiles; ++it) {
-                const int buf = it & 1;
+                const int buf = it & 1;          // barrier pair of this tile (its T-epilogue group)
                 if (lane == 0) stamp(it, 1);
-                mbar_wait(bar(BAR_TACC_EMPTY + buf), (uint32_t)((it >> 1) & 1) ^ 1u);
+                {   // accumulator drained by tile it-2, first x chunk landed: probe both so their latencies overlap
+                    const uint32_t b1 = bar(BAR_TACC_EMPTY + buf), p1 = (uint32_t)((it >> 1) & 1) ^ 1u;
+                    const uint32_t ok1 = mbar_try_wait(b1, p1), ok2 = mbar_try_wait(bar(BAR_XFULL + xs), xph);
+                    if (!ok1) mbar_wait(b1, p1);
+                    (void)ok2;
+                }
                 tc_fence_after_sync();
                 const uint32_t d = tmem_T + buf * 64;
                 for (int ch = 0; ch < p.nch; ++ch) {
@@ -245,6 +266,7 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                     const uint64_t a0 = xdesc + ((base + p.off_x + xs * p.x_stage) >> 4);
                     const uint64_t b0 = xdesc + ((base + p.off_v + (p.resident ? ch : xs) * p.v_chunk) >> 4);
                     if (elect_one()) {
+                        if (!(p.debug & 128))
 #pragma unroll
                         for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
@@ -260,73 +282,109 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 if (lane == 0) stamp(it, 3);
             }
         }
-    } else if (warp == 10) {
+    } else if (warp == 10 || (warp == 15 && p.resident && p.nn2 == 1)) {
         // =========================== GEMM2 issuer (A = bf16 T in TMEM, B = Wh tap slot in smem) ===========================
+        // With resident weights and a single N-tile per tile (the 64-channel layers) the even and the odd tiles form two
+        // independent pipelines (own T accumulator, A buffer, Y accumulator, epilogue groups), so they also get an issuing
+        // warp each — warp 10 and the otherwise idle Wh producer warp 15: the per-tile barrier latencies of one issuer
+        // (~750 cycles) then overlap the other's MMAs instead of idling the tensor pipe.
+        const bool split = p.resident && p.nn2 == 1;
+        const int j0 = split ? (warp == 15 ? 1 : 0) : 0, jstep = split ? 2 : 1;
         if (my_tiles > 0) {
             constexpr uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT2 >> 3) << 17) | (8u << 24);
             constexpr uint64_t hdesc = desc_hi(16, 8 * HROW, swz_type(HROW));
-            int q = 0;                       // N-tile counter (Y accumulator index)
             int hs = 0; uint32_t hph = 0;    // Wh ring
             if (p.resident) { mbar_wait(bar(BAR_WFULL), 0); tc_fence_after_sync(); }
-            for (int j = 0; j < my_tiles; ++j) {
+            for (int j = j0; j < my_tiles; j += jstep) {
                 if (lane == 0) stamp(j, 4);
-                mbar_wait(bar(BAR_TA_FULL), (uint32_t)(j & 1));
+                const int ab = j & 1;
+                int q = j * p.nn2;           // N-tile counter (Y accumulator index)
+                {   // both barriers are usually complete already: probe them together so their latencies overlap
+                    const uint32_t b1 = bar(BAR_TA_FULL + ab), p1 = (uint32_t)((j >> 1) & 1);
+                    const uint32_t b2 = bar(BAR_YACC_EMPTY + (q & 1)), p2 = (uint32_t)((q >> 1) & 1) ^ 1u;
+                    const uint32_t ok1 = mbar_try_wait(b1, p1), ok2 = mbar_try_wait(b2, p2);
+                    if (!ok1) mbar_wait(b1, p1);
+                    if (!ok2) mbar_wait(b2, p2);
+                }
                 tc_fence_after_sync();
                 if (lane == 0) stamp(j, 5);
                 for (int n2 = 0; n2 < p.nn2; ++n2, ++q) {
                     const int yb = q & 1;
-                    mbar_wait(bar(BAR_YACC_EMPTY + yb), (uint32_t)((q >> 1) & 1) ^ 1u);
-                    tc_fence_after_sync();
+                    if (n2 > 0) {
+                        mbar_wait(bar(BAR_YACC_EMPTY + yb), (uint32_t)((q >> 1) & 1) ^ 1u);
+                        tc_fence_after_sync();
+                    }
+                    if (lane == 0 && n2 == 0) stamp(j, 16);
                     const uint32_t d = tmem_Y + yb * NT2;
-#pragma unroll
-                    for (int dx = 0; dx < 3; ++dx) {
-                        uint32_t hb;
-                        if (p.resident) {
-                            hb = base + p.off_h + (n2 * 3 + dx) * p.h_slot;
-                        } else {
-                            mbar_wait(bar(BAR_HFULL + hs), hph);
-                            tc_fence_after_sync();
-                            hb = base + p.off_h + hs * p.h_slot;
-                        }
-                        const uint64_t b0 = hdesc + (hb >> 4);
+                    if (p.resident) {
+                        const uint64_t b0 = hdesc + ((base + p.off_h + n2 * 3 * p.h_slot) >> 4);
+                        const uint32_t slot16 = p.h_slot >> 4;
                         if (elect_one()) {
 #pragma unroll
-                            for (int kk = 0; kk < KP / 16; ++kk)
-                                umma_bf16_ts(d, tmem_A + dx * ACOLS + kk * 8, b0 + ((kk * 32) >> 4), idesc2, (uint32_t)((dx | kk) != 0));
-                            if (!p.resident) umma_commit(bar(BAR_HEMPTY + hs));
-                            if (dx == 2) {
-                                umma_commit(bar(BAR_YACC_FULL + yb));
-                                if (n2 == p.nn2 - 1) umma_commit(bar(BAR_TA_EMPTY));
-                            }
+                            for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+                                for (int kk = 0; kk < KP / 16; ++kk)
+                                    umma_bf16_ts(d, tmem_A + (NABUF == 2 ? ab * 96 : 0) + dx * ACOLS + kk * 8, b0 + dx * slot16 + ((kk * 32) >> 4),
+                                                 idesc2, (uint32_t)((dx | kk) != 0));
+                            umma_commit(bar(BAR_YACC_FULL + yb));
+                            if (n2 == p.nn2 - 1) umma_commit(bar(BAR_TA_EMPTY + ab));
                         }
                         __syncwarp();
-                        if (!p.resident && ++hs == p.hslots) { hs = 0; hph ^= 1u; }
+                    } else {
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            mbar_wait(bar(BAR_HFULL + hs), hph);
+                            tc_fence_after_sync();
+                            const uint64_t b0 = hdesc + ((base + p.off_h + hs * p.h_slot) >> 4);
+                            if (elect_one()) {
+#pragma unroll
+                                for (int kk = 0; kk < KP / 16; ++kk)
+                                    umma_bf16_ts(d, tmem_A + (NABUF == 2 ? ab * 96 : 0) + dx * ACOLS + kk * 8, b0 + ((kk * 32) >> 4), idesc2,
+                                                 (uint32_t)((dx | kk) != 0));
+                                umma_commit(bar(BAR_HEMPTY + hs));
+                                if (dx == 2) {
+                                    umma_commit(bar(BAR_YACC_FULL + yb));
+                                    if (n2 == p.nn2 - 1) umma_commit(bar(BAR_TA_EMPTY + ab));
+                                }
+                            }
+                            __syncwarp();
+                            if (++hs == p.hslots) { hs = 0; hph ^= 1u; }
+                        }
                     }
+                    if (lane == 0 && n2 == p.nn2 - 1) stamp(j, 17);
                 }
             }
         }
-    } else if (warp < 6) {
-        // =========================== T-epilogue warps (2..5) ===========================
+    } else if (warp < 6 || warp >= 16) {
+        // =========================== T-epilogue warps: group 0 = warps 2..5 (even tiles), group 1 = warps 16..19 (odd tiles) ===========================
         // GEMM1 accumulator (fp32, TMEM) -> bf16 -> three lane-shifted copies back into TMEM (the A operand of GEMM2).
+        const int tg = warp >= 16 ? 1 : 0;
         const int lg = warp & 3;                 // TMEM lane group this warp may access
         const uint32_t lane_addr = (uint32_t)(lg * 32) << 16;
-        for (int it = 0; it < my_tiles; ++it) {
-            const int buf = it & 1;
-            mbar_wait(bar(BAR_TACC_FULL + buf), (uint32_t)((it >> 1) & 1));
+        const bool stamper = (warp == 2 || warp == 16) && lane == 0;
+        const uint32_t tacc = tmem_T + tg * 64 + lane_addr;
+        const uint32_t ta = tmem_A + (NABUF == 2 ? tg * 96 : 0) + lane_addr;
+        for (int it = tg; it < my_tiles; it += 2) {
+            const uint32_t ph = (uint32_t)((it >> 1) & 1);
+            mbar_wait(bar(BAR_TACC_FULL + tg), ph);
             tc_fence_after_sync();
-            if (threadIdx.x == 64) stamp(it, 6);
+            if (stamper) stamp(it, 6);
             uint32_t v[KP];
 #pragma unroll
-            for (int c16 = 0; c16 < KP / 16; ++c16) tmem_ld16(tmem_T + buf * 64 + lane_addr + c16 * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[c16 * 16]));
+            for (int c16 = 0; c16 < KP / 16; ++c16) tmem_ld16(tacc + c16 * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[c16 * 16]));
             tmem_ld_wait();
+            if (stamper) stamp(it, 10);
             tc_fence_before_sync();
-            mbar_arrive(bar(BAR_TACC_EMPTY + buf));          // accumulator drained: GEMM1 of tile it+2 may start
+            mbar_arrive(bar(BAR_TACC_EMPTY + tg));            // accumulator drained: the next GEMM1 into it may start
             uint32_t pk[ACOLS];                               // column c holds k = 2c (low half) and 2c+1 (high half)
 #pragma unroll
             for (int c = 0; c < ACOLS; ++c) pk[c] = pack_bf16(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]));
-            mbar_wait(bar(BAR_TA_EMPTY), (uint32_t)(it & 1) ^ 1u);   // GEMM2 of tile it-1 has finished reading the copies
+            // the A buffer must have been read: by GEMM2 of tile it-2 (two buffers) or of tile it-1 (one, the other group's)
+            if (NABUF == 2) mbar_wait(bar(BAR_TA_EMPTY + tg), ph ^ 1u);
+            else if (it > 0) mbar_wait(bar(BAR_TA_EMPTY + (tg ^ 1)), (uint32_t)(((it - 1) >> 1) & 1));
             tc_fence_after_sync();
-            const uint32_t ta = tmem_A + lane_addr;
+            if (stamper) stamp(it, 11);
+            if (!(p.debug & 32))
 #pragma unroll
             for (int c8 = 0; c8 < ACOLS / 8; ++c8) {
                 uint32_t up[8], dn[8];
@@ -339,11 +397,14 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 tmem_st8(ta + 1 * ACOLS + c8 * 8, *reinterpret_cast<uint32_t(*)[8]>(&pk[c8 * 8]));
                 tmem_st8(ta + 2 * ACOLS + c8 * 8, dn);
             }
+            if (stamper) stamp(it, 12);
             tmem_st_wait();
             tc_fence_before_sync();
-            mbar_arrive(bar(BAR_TA_FULL));
-            if (threadIdx.x == 64) stamp(it, 7);
+            mbar_arrive(bar(BAR_TA_FULL + tg));
+            if (stamper) stamp(it, 7);
         }
+    } else if (warp == 15) {
+        // resident weights and several N-tiles per tile: nothing to do for this warp
     } else {
         // =========================== Y-epilogue warps: group 0 = warps 6..9, group 1 = warps 11..14 ===========================
         // GEMM2 accumulator -> +bias, ReLU -> bf16 -> swizzled staging [-> 2x2 max-pool] -> TMA store, 64 channels per item.
@@ -377,34 +438,49 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             if (et == 0 && n2 == 0) stamp(j, 8);
             const uint32_t tacc = tmem_Y + yb * NT2 + (NT2 == 64 ? 0 : g * 64) + lane_addr;
             uint32_t v[kNT];
+            if (p.debug & 64) {
 #pragma unroll
-            for (int c16 = 0; c16 < kNT / 16; ++c16) tmem_ld16(tacc + c16 * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[c16 * 16]));
+                for (int c = 0; c < kNT; ++c) v[c] = 0;
+            } else {
+#pragma unroll
+                for (int c16 = 0; c16 < kNT / 16; ++c16) tmem_ld16(tacc + c16 * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[c16 * 16]));
+            }
             tmem_ld_wait();
+            if (et == 0 && n2 == 0) stamp(j, 13);
             tc_fence_before_sync();
             mbar_arrive(bar(BAR_YACC_EMPTY + yb));       // accumulator drained: GEMM2 of N-tile q+2 may start
-            uint32_t w[kNT / 2];
-            {
-                const float* bz = sbias + chan0;
-#pragma unroll
-                for (int ch = 0; ch < kNT / 8; ++ch) {
-                    float4 b0 = ld_shared_f4(bz + ch * 8), b1 = ld_shared_f4(bz + ch * 8 + 4);
-                    w[ch * 4 + 0] = pack_bf16(fmaxf(__uint_as_float(v[ch * 8 + 0]) + b0.x, lo), fmaxf(__uint_as_float(v[ch * 8 + 1]) + b0.y, lo));
-                    w[ch * 4 + 1] = pack_bf16(fmaxf(__uint_as_float(v[ch * 8 + 2]) + b0.z, lo), fmaxf(__uint_as_float(v[ch * 8 + 3]) + b0.w, lo));
-                    w[ch * 4 + 2] = pack_bf16(fmaxf(__uint_as_float(v[ch * 8 + 4]) + b1.x, lo), fmaxf(__uint_as_float(v[ch * 8 + 5]) + b1.y, lo));
-                    w[ch * 4 + 3] = pack_bf16(fmaxf(__uint_as_float(v[ch * 8 + 6]) + b1.z, lo), fmaxf(__uint_as_float(v[ch * 8 + 7]) + b1.w, lo));
-                }
-            }
-            // this group's staging buffer was handed to a TMA store one item ago: wait until it has been read
+            // this group's staging buffer was handed to a TMA store one item ago: make sure it has been read
+            // (waited for here, after the TMEM load, so that the store's smem read overlaps the load)
             if (et == 0) tma_store_wait_read<0>();
             named_bar_sync(bar_a, 128);
+            if (et == 0 && n2 == 0) stamp(j, 14);
             if (valid && !(p.debug & 2)) {
+                // bias chunks are fetched two chunks ahead of their use: a shared-memory load issued right before its
+                // first use costs the whole load latency eight times per item (short-scoreboard stalls in the profile)
+                const uint32_t bz = smem_u32(sbias + chan0);
+                float4 bq[4];
+                bq[0] = ld_shared_f4_relaxed(bz); bq[1] = ld_shared_f4_relaxed(bz + 16);
+                bq[2] = ld_shared_f4_relaxed(bz + 32); bq[3] = ld_shared_f4_relaxed(bz + 48);
 #pragma unroll
-                for (int ch = 0; ch < kNT / 8; ++ch)
-                    st_shared_v4(sb + row_off + (((uint32_t)ch ^ sw) << 4), w[ch * 4], w[ch * 4 + 1], w[ch * 4 + 2], w[ch * 4 + 3]);
+                for (int ch = 0; ch < kNT / 8; ++ch) {
+                    const float4 b0 = bq[(2 * ch) & 3], b1 = bq[(2 * ch + 1) & 3];
+                    if (ch + 2 < kNT / 8) {
+                        bq[(2 * ch) & 3] = ld_shared_f4_relaxed(bz + (ch + 2) * 32);
+                        bq[(2 * ch + 1) & 3] = ld_shared_f4_relaxed(bz + (ch + 2) * 32 + 16);
+                    }
+                    st_shared_v4_relaxed(sb + row_off + (((uint32_t)ch ^ sw) << 4),
+                                         pack_bf16(fmaxf(__uint_as_float(v[ch * 8 + 0]) + b0.x, lo), fmaxf(__uint_as_float(v[ch * 8 + 1]) + b0.y, lo)),
+                                         pack_bf16(fmaxf(__uint_as_float(v[ch * 8 + 2]) + b0.z, lo), fmaxf(__uint_as_float(v[ch * 8 + 3]) + b0.w, lo)),
+                                         pack_bf16(fmaxf(__uint_as_float(v[ch * 8 + 4]) + b1.x, lo), fmaxf(__uint_as_float(v[ch * 8 + 5]) + b1.y, lo)),
+                                         pack_bf16(fmaxf(__uint_as_float(v[ch * 8 + 6]) + b1.z, lo), fmaxf(__uint_as_float(v[ch * 8 + 7]) + b1.w, lo)));
+                }
             }
             if (!p.pool) {
-                fence_proxy_async_smem();
+                if (et == 0 && n2 == 0) stamp(j, 18);
+                if (!(p.debug & 8)) fence_proxy_async_smem();
+                if (et == 0 && n2 == 0) stamp(j, 19);
                 named_bar_sync(bar_b, 128);
+                if (et == 0 && n2 == 0) stamp(j, 15);
                 if (et == 0 && !(p.debug & 1)) {
                     tma_store_4d(&tm_y, sb, chan0, t.w0, t.h0, t.b);
                     tma_store_commit();

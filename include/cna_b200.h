@@ -99,10 +99,11 @@ int cna_lowrank2_pack(const float* v_w /*(K,C,d,1)*/, const float* h_w /*(N,K,1,
 int cna_lowrank2_fused_forward(const void* x, const void* wv_packed, const void* wh_packed, const float* bias,
                                void* y, int B, int H, int W, int c_pad, int k_pad, int N, int d,
                                int relu, int pool, void* stream);
-/* Diagnostic variant: CTA 0 additionally records clock64() stamps, 10 per tile for its first `trace_tiles` tiles
- * (`trace` holds trace_tiles + 1 rows of 10; the last row = {clock64, globaltimer} at CTA 0's start and end)
+/* Diagnostic variant: CTA 0 additionally records clock64() stamps, 20 per tile for its first `trace_tiles` tiles
+ * (`trace` holds trace_tiles + 1 rows of 20; the last row = {clock64, globaltimer} at CTA 0's start and end)
  * (0 x issued, 1 GEMM1 turn, 2 x landed, 3 GEMM1 issued, 4 GEMM2 turn, 5 T ready, 6 T-epilogue start, 7 T stored,
- * 8 Y-epilogue start, 9 y store issued).  Used by benchmarks/trace_lowrank2.py to read the pipeline's critical path. */
+ * 8 Y-epilogue start, 9 y store issued, 10 T loaded from TMEM, 11 A buffer free, 12 A copies issued, 13 Y loaded from TMEM,
+ * 14 staging buffer free, 15 y staged, 16 GEMM2 got its accumulator, 17 GEMM2 issued).  Used by benchmarks/trace_lowrank2.py to read the pipeline's critical path. */
 int cna_lowrank2_fused_forward_traced(const void* x, const void* wv_packed, const void* wh_packed, const float* bias,
                                       void* y, int B, int H, int W, int c_pad, int k_pad, int N, int d, int relu,
                                       void* stream, long long* trace, int trace_tiles);

@@ -27,6 +27,9 @@ _SIGS = {
     "cna_pack_dw_weight": "ppiiiip",
     "cna_conv_taps_forward": "pppppiiiiiiiiiiiip",
     "cna_dwconv_forward": "ppppippiiiiiiiiiiiip",
+    "cna_conv1x1_tc_supported": "ii",
+    "cna_conv1x1_pack": "ppiip",
+    "cna_conv1x1_tc_forward": "pppppLiiip",
     "cna_fix_padding_bias": "ppiiiiiip",
     "cna_add": "pppLip",
     "cna_lowrank2_pack": "ppppiiiiiip",
@@ -207,6 +210,35 @@ def conv_taps(x, wpk, bias, N, taps, axis, stride=(1, 1), pad=0, relu=False, gat
     with torch.cuda.device(x.device):
         _check(lib().cna_conv_taps_forward(_p(x), _p(wpk), _p(bias), _p(gate), _p(y), B, H, W, C, N, taps, axis,
                                            sh, sw, pad, int(relu), dtype_code(x.dtype), _stream(x)))
+    return y
+
+
+def conv1x1_tc_supported(C: int, N: int) -> bool:
+    return bool(lib().cna_conv1x1_tc_supported(int(C), int(N)))
+
+
+def conv1x1_pack(w: torch.Tensor) -> torch.Tensor:
+    """(N,C,1,1) conv weight -> bf16 [N][C] (the K-major B operand of the tcgen05 1x1 conv)."""
+    _ready(w)
+    N, C = w.shape[:2]
+    out = torch.empty((N, C), device=w.device, dtype=torch.bfloat16)
+    wf = _f32c(w)
+    with torch.cuda.device(w.device):
+        _check(lib().cna_conv1x1_pack(_p(wf), _p(out), N, C, _stream(w)))
+    return out
+
+
+def conv1x1_tc(x, w_nc, bias, relu=False, gate=None):
+    """x (B,H,W,C) bf16 NHWC, w_nc bf16 [N][C], bias fp32 (N,) or None -> (B,H,W,N) bf16 [* gate]."""
+    _ready(x)
+    Bn, H, W, C = x.shape
+    N = w_nc.shape[0]
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and w_nc.shape == (N, C) and w_nc.dtype == torch.bfloat16
+    y = torch.empty((Bn, H, W, N), device=x.device, dtype=torch.bfloat16)
+    if gate is not None:
+        assert gate.shape == y.shape and gate.dtype == x.dtype and gate.is_contiguous()
+    with torch.cuda.device(x.device):
+        _check(lib().cna_conv1x1_tc_forward(_p(x), _p(w_nc), _p(bias), _p(gate), _p(y), Bn * H * W, C, N, int(relu), _stream(x)))
     return y
 
 

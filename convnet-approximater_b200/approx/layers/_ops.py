@@ -61,6 +61,10 @@ def dense_taps(conv: nn.Conv2d, x, relu=False, gate=None):
     pad = conv.padding[0] if axis == 0 else conv.padding[1]
     other = conv.padding[1] if axis == 0 else conv.padding[0]
     assert other == 0, "padding across the tap axis is not used on this path"
+    if (taps == 1 and x.dtype == torch.bfloat16 and tuple(conv.stride) == (1, 1) and pad == 0 and x.is_contiguous()
+            and B.conv1x1_tc_supported(conv.in_channels, conv.out_channels)):
+        w_nc = cached(conv, "w_1x1_tc", (conv.weight,), torch.bfloat16, lambda: B.conv1x1_pack(conv.weight))
+        return B.conv1x1_tc(x, w_nc, bias_f32(conv), relu=relu, gate=gate)       # tcgen05 path
     wpk = cached(conv, "taps_w", (conv.weight,), x.dtype, lambda: B.pack_taps(conv.weight, x.dtype))
     return B.conv_taps(x, wpk, bias_f32(conv), conv.out_channels, taps, axis, tuple(conv.stride), pad,
                        relu=relu, gate=gate)

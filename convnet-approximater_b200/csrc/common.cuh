@@ -37,6 +37,11 @@ void count_launch(int n = 1);
         ::cna::count_launch();                                                          \
     } while (0)
 
+// dwconv_tile.cu: register-tiled depthwise kernels for the MSCA shapes; *handled = false -> use the generic kernel
+int dw_tile_try(const void* x, const void* w_packed, const float* bias, const float* res, int res_p, const void* add, void* y,
+                int B, int H, int W, int Cin, int mult, int kh, int kw, int sh, int sw, int ph, int pw, int dtype, cudaStream_t st,
+                bool* handled);
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }

@@ -5,6 +5,8 @@
 // kernel size / stride / padding); the MSCA-specific fused kernels live in msca.cu.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace cna {
 
 template <typename T>
@@ -123,6 +125,16 @@ int cna_dwconv_forward(const void* x, const void* w_packed, const float* bias, c
     long long total = (long long)B * Ho * Wo * Cin * mult;
     int grid = (int)std::min<long long>(ceil_div_ll(total, 256), 148LL * 64);
     cudaStream_t st = as_stream(stream);
+    if (getenv("CNA_DW_GENERIC") == nullptr) {      // (diagnostic switch: force the generic kernel)
+        bool handled = false;
+        if (dw_tile_try(x, w_packed, bias, res, res_p, add, y, B, H, W, Cin, mult, kh, kw, stride_h, stride_w, pad_h, pad_w, dtype, st,
+                        &handled))
+            return 1;
+        if (handled) {
+            CNA_LAUNCH_OK();
+            return 0;
+        }
+    }
     if (dtype == CNA_F32)
         dwconv_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (const float*)w_packed, bias, res, res_p, (const float*)add,
                                                       (float*)y, B, H, W, Cin, mult, Ho, Wo, kh, kw, stride_h, stride_w, pad_h, pad_w);

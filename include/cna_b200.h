@@ -64,6 +64,16 @@ int cna_conv_taps_forward(const void* x, const void* w_packed, const float* bias
                           int B, int H, int W, int C, int N, int taps, int axis,
                           int stride_h, int stride_w, int pad, int relu, int dtype, void* stream);
 
+/* 1x1 convolution on tcgen05 (bf16 NHWC, fp32 accumulation): y[p][n] = act(sum_c a[p][c] * w[n][c] + bias[n]) [* gate[p][n]]
+ * over P = B*H*W pixels.  w_packed = the (N, C, 1, 1) conv weight as bf16 (cna_conv1x1_pack).  gate may be NULL; with a gate
+ * the conv output is rounded to bf16 before the multiply, as the reference's two materialised tensors are.
+ * Replaces nn.Conv2d(C, N, 1) at src/approx/layers/msca.py:23,26 (channel_mix and the `x *` gate) and
+ * src/approx/layers/low_rank_conv.py:49,52 (d_conv) for bf16 tensors; cna_conv_taps_forward stays the fp32 / any-shape path. */
+int cna_conv1x1_tc_supported(int C, int N);
+int cna_conv1x1_pack(const float* w_nc, void* packed, int N, int C, void* stream);
+int cna_conv1x1_tc_forward(const void* a, const void* w_packed, const float* bias, const void* gate, void* y, long long P, int C,
+                           int N, int relu, void* stream);
+
 /* ---- depthwise convolution (generic) -------------------------------------------------------- */
 /* Grouped conv with groups=Cin and channel multiplier `mult`: output channel co reads input channel co/mult.
  * w_packed[kh*kw][Cin*mult]; bias may be NULL.

@@ -87,6 +87,17 @@ DW_CASES = [
     (2, 8, 7, 9, 1, 21, 1, 1, 1, 10, 0),
     (1, 5, 7, 9, 1, 21, 21, 1, 1, 10, 10),
     (2, 6, 10, 8, 2, 3, 1, 2, 1, 1, 0),
+    # register-tiled kernels (dwconv_tile.cu): C % 32 == 0, stride 1, 'same' padding, MSCA's kernel sizes, ragged tiles
+    (2, 32, 19, 37, 1, 5, 5, 1, 1, 2, 2),
+    (1, 64, 33, 18, 1, 21, 21, 1, 1, 10, 10),
+    (2, 32, 7, 7, 1, 21, 21, 1, 1, 10, 10),
+    (2, 32, 20, 35, 1, 1, 7, 1, 1, 0, 3),
+    (2, 32, 35, 20, 1, 7, 1, 1, 1, 3, 0),
+    (1, 96, 16, 40, 1, 1, 11, 1, 1, 0, 5),
+    (1, 32, 40, 16, 1, 11, 1, 1, 1, 5, 0),
+    (2, 32, 17, 50, 1, 1, 21, 1, 1, 0, 10),
+    (2, 160, 32, 32, 1, 21, 1, 1, 1, 10, 0),
+    (2, 32, 18, 18, 1, 3, 3, 1, 1, 1, 1),
 ]
 
 
@@ -139,3 +150,25 @@ def test_errors_are_loud(B):
         MSCA(8, 5, (7, 11, 21))(torch.randn(1, 8, 8, 8))
     with pytest.raises(RuntimeError, match="cna_b200"):
         B._check(B.lib().cna_conv_taps_forward(0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 0, 1, 1, 0, 0, 0, 0))
+
+
+@pytest.mark.parametrize("case", [(2, 32, 9, 13, 32, True), (1, 160, 16, 16, 160, True), (2, 64, 7, 5, 48, False),
+                                  (1, 256, 12, 11, 256, True), (3, 96, 5, 5, 16, False)])
+def test_conv1x1_tcgen05(B, case):
+    """tcgen05 1x1 conv (+bias, +gate / ReLU) against the bf16 torch reference of channel_mix / d_conv."""
+    Bn, C, H, W, N, gated = case
+    torch.manual_seed(11)
+    x = torch.randn(Bn, C, H, W).bfloat16()
+    w = (torch.randn(N, C, 1, 1) / C ** 0.5).bfloat16()
+    b = torch.randn(N).bfloat16()
+    assert B.conv1x1_tc_supported(C, N)
+    xn = B.to_nhwc(x.cuda()).contiguous()
+    w_nc = B.conv1x1_pack(w.cuda().float())
+    if gated:
+        g = torch.randn(Bn, N, H, W).bfloat16()
+        ref = g * F.conv2d(x, w, b)
+        y = B.conv1x1_tc(xn, w_nc, b.float().cuda(), gate=B.to_nhwc(g.cuda()).contiguous())
+    else:
+        ref = torch.relu(F.conv2d(x, w, b))
+        y = B.conv1x1_tc(xn, w_nc, b.float().cuda(), relu=True)
+    assert O.compare4d(ref.float(), nchw(y)) < TOL16

@@ -51,56 +51,74 @@ def algorithmic_flops_per_image(K):
     return sum(2 * H * H * 3 * C * K + 2 * H * H * 3 * K * N for (C, N, H) in VGG)
 
 
-class ClockSampler:
-    """Samples SM clock, power and throttle reasons through NVML every few ms while the timed region runs
-    (the timed region is tens of ms, far below nvidia-smi's own sampling period)."""
+_SAMPLER_SRC = r"""
+import sys, time
+import pynvml as nv
+nv.nvmlInit()
+h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+print("max", nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM), flush=True)
+while True:
+    print(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetPowerUsage(h) / 1000.0,
+          nv.nvmlDeviceGetCurrentClocksEventReasons(h), flush=True)
+    time.sleep(0.002)
+"""
 
-    def __init__(self, index, period_s=0.002):
-        self.index, self.period, self.rows, self.stop_evt, self.t, self.err = index, period_s, [], threading.Event(), None, None
+
+class ClockSampler:
+    """Samples SM clock, power and throttle reasons through NVML every ~2 ms while the timed region runs.  It is a
+    separate process: a thread of this one starves behind the launch loop (GIL), and nvidia-smi's own sampling period
+    is longer than the timed region."""
+
+    def __init__(self, index):
+        self.index, self.proc, self.rows, self.mx, self.err = index, None, [], None, None
 
     def start(self):
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
             phys = self.index
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
             if visible:
                 ids = [v.strip() for v in visible.split(",") if v.strip()]
                 if self.index < len(ids) and ids[self.index].isdigit():
                     phys = int(ids[self.index])
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
-            self.nv = pynvml
-            self.mx = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(phys)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            first = self.proc.stdout.readline().split()           # blocks until NVML is up: sampling has started
+            self.mx = int(first[1]) if len(first) == 2 and first[0] == "max" else None
+            self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception as e:  # noqa: BLE001
-            self.err = f"nvml unavailable: {e}"
+            self.err, self.proc = f"nvml sampler unavailable: {e}", None
 
-    def _poll(self):
-        nv = self.nv
-        while not self.stop_evt.is_set():
-            try:
-                self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
-                                  nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0,
-                                  nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)))
-            except Exception as e:  # noqa: BLE001
-                self.err = str(e)
-                return
-            time.sleep(self.period)
+    def _read(self):
+        for line in self.proc.stdout:
+            f = line.split()
+            if len(f) == 3:
+                try:
+                    self.rows.append((int(f[0]), float(f[1]), int(f[2])))
+                except ValueError:
+                    pass
 
-    def stop(self):
-        if self.t is None:
+    def mark(self):
+        """Number of samples so far (call at the start of the timed region)."""
+        return len(self.rows)
+
+    def stop(self, first=0):
+        if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "not started"], "samples": 0}
-        self.stop_evt.set()
+        time.sleep(0.01)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
         self.t.join(timeout=2)
-        nv = self.nv
-        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
-                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap,
-                 "hw_power_brake": nv.nvmlClocksEventReasonHwPowerBrakeSlowdown}
-        sm = sorted(r[0] for r in self.rows)
-        reasons = sorted(n for n, bit in names.items() if any(r[2] & bit for r in self.rows))
+        rows = self.rows[first:]
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                "hw_power_brake": 0x80}
+        sm = sorted(r[0] for r in rows)
+        reasons = sorted(n for n, bit in bits.items() if any(r[2] & bit for r in rows))
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx, "reasons": reasons,
-                "power_w_max": max((r[1] for r in self.rows), default=None), "samples": len(sm)}
+                "power_w_max": max((r[1] for r in rows), default=None), "samples": len(sm)}
 
 
 def cpu_reference_run(rank_k, sample_batch, iters, warmup, threads=None):
@@ -210,6 +228,7 @@ def run_ours(args):
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
+        s0 = sampler.mark()
         n0 = B.launch_count()
         t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_beg.record()
@@ -220,7 +239,7 @@ def run_ours(args):
         launches = B.launch_count() - n0
         ms = t_beg.elapsed_time(t_end)
         conv_ms = sum(a.elapsed_time(b) for row in ev for (a, b) in row)
-        clocks = sampler.stop() if rank == 0 else None
+        clocks = sampler.stop(s0) if rank == 0 else None
 
         # ---- end to end through the public API with HOST buffers: every step copies its (pinned) NCHW bf16 images
         # to the device, runs the trunk module (layout conversion included) and reads the result back to the host.
@@ -258,6 +277,13 @@ def run_ours(args):
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         tc_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         alg_bytes = algorithmic_bytes_per_image(K) * Bsz            # per step (13 launches)
+        traffic = None                                               # measured DRAM bytes per launch (ncu --set full), if captured
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_fused_conv_traffic.json")))
+            if tj.get("rank") == K and tj.get("batch") == Bsz:
+                traffic = tj["dram_bytes_per_step"] / len(VGG)
+        except Exception:  # noqa: BLE001
+            pass
         achieved = alg_bytes * args.steps / (conv_ms * 1e-3) / 1e9   # GB/s over the fused-conv launches only
         tflops = algorithmic_flops_per_image(K) * Bsz * args.steps / (conv_ms * 1e-3) / 1e12
         line = {
@@ -271,8 +297,8 @@ def run_ours(args):
                     "h2d_bytes_per_step": x_host.numel() * 2, "d2h_bytes_per_step": y_host.numel() * 2},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "lowrank2_fused_kernel (13 launches/step)",
-                         "algorithmic_bytes_per_step": alg_bytes, "tensor_tflops": tflops,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "lowrank2_fused_kernel (13 launches/step)",
+                         "algorithmic_bytes_per_launch": alg_bytes / len(VGG), "algorithmic_bytes_per_step": alg_bytes, "tensor_tflops": tflops,
                          "tensor_frac_of_sustained_peak": tflops / tc_peak,
                          "fused_conv_share_of_step": conv_ms / ms},
             "clocks": clocks,

@@ -13,6 +13,8 @@
 // generic kernel (dwconv.cu), with the same rounding points.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace cna {
 
 constexpr int kDT = 16;        // tile edge (outputs) and run length per thread
@@ -160,6 +162,146 @@ dw_tile_kernel(const T* __restrict__ x, const T* __restrict__ w /*[KH*KW][C]*/, 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// 1-D strips (1 x K along W, K x 1 along H): HBM-bound for K = 7 / 11 (7-11 MAC per element against 4 bytes), so the
+// design goal is few INSTRUCTIONS per element (a B200 SM can issue ~22 thread-instructions per element at the HBM rate):
+// no shared memory at all — a thread owns 4 channels (one 8-byte bf16 / 16-byte fp32 vector) and a run of 16 (8 for K > 7) outputs
+// along the strip axis, keeps the K + 15 inputs it needs in a register window (each loaded and unpacked once, straight
+// from global memory; neighbouring runs' halo re-reads hit L1/L2) and its 4 x K weights in registers:
+// ~11 (K = 7) to ~28 (K = 21) instructions per element.  Lanes run over channel groups, then pixels, so loads coalesce.
+// ------------------------------------------------------------------------------------------------
+template <int K> struct StripRun { static constexpr int value = K <= 7 ? 16 : 8; };   // outputs per thread along the strip axis
+
+// Blackwell's packed fp32 FMA (SASS FFMA2): two independent fp32 FMAs per issued instruction — the same FLOPs per FMA-pipe
+// cycle, half the issue slots, which is what an instruction-issue-bound streaming kernel is short of.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                       rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+
+template <typename T> struct Vec4;
+template <> struct Vec4<__nv_bfloat16> {
+    using Raw = uint2;
+    static __device__ __forceinline__ void unpack(uint2 v, float (&f)[4]) {
+        f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+        f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+    }
+    static __device__ __forceinline__ uint2 pack(const float (&f)[4]) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b = __floats2bfloat162_rn(f[2], f[3]);
+        return make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    }
+    static __device__ __forceinline__ float round(float a) { return __bfloat162float(__float2bfloat16_rn(a)); }
+    static __device__ __forceinline__ uint2 zero() { return make_uint2(0u, 0u); }
+};
+template <> struct Vec4<float> {
+    using Raw = float4;
+    static __device__ __forceinline__ void unpack(float4 v, float (&f)[4]) { f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
+    static __device__ __forceinline__ float4 pack(const float (&f)[4]) { return make_float4(f[0], f[1], f[2], f[3]); }
+    static __device__ __forceinline__ float round(float a) { return a; }
+    static __device__ __forceinline__ float4 zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+};
+
+template <typename T, int K, bool ALONG_W, bool EXTRAS>
+__global__ void __launch_bounds__(256, K >= 21 ? 2 : 1)
+dw_strip_kernel(const T* __restrict__ x, const T* __restrict__ w /*[K][C]*/, const float* __restrict__ bias,
+                const float* __restrict__ res, int res_p, const T* __restrict__ add, T* __restrict__ y,
+                int B, int H, int W, int C, long long nitems) {
+    constexpr int kSR = StripRun<K>::value;
+    using V = Vec4<T>;
+    using Raw = typename V::Raw;
+    constexpr int P = K / 2;
+    const int ncg = C >> 2;                                   // channel groups of 4
+    const int L = ALONG_W ? W : H;                            // length of the strip axis
+    const int lines = ALONG_W ? H : W;                        // lines across it
+    const int runs = (L + kSR - 1) / kSR;
+    const size_t step = ALONG_W ? (size_t)C : (size_t)W * C;  // element stride along the strip axis
+    // 32-bit index arithmetic (the launcher guarantees nitems < 2^31): 64-bit div/mod would cost more than the convolution
+    const uint32_t n32 = (uint32_t)nitems, stride32 = gridDim.x * blockDim.x;
+    for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < n32; it += stride32) {
+        // item order: channel group fastest, then (ALONG_W: run, line | ALONG_H: line, run), then image
+        const uint32_t cg = it % (uint32_t)ncg;
+        uint32_t r = it / (uint32_t)ncg;
+        uint32_t run, line;
+        if (ALONG_W) { run = r % (uint32_t)runs; r /= (uint32_t)runs; line = r % (uint32_t)lines; r /= (uint32_t)lines; }
+        else         { line = r % (uint32_t)lines; r /= (uint32_t)lines; run = r % (uint32_t)runs; r /= (uint32_t)runs; }
+        const int b = (int)r;
+        const int c = (int)cg * 4;
+        const int s0 = (int)run * kSR;                        // first output along the strip axis
+        const size_t base = ALONG_W ? (((size_t)b * H + line) * W) * C + c : (((size_t)b * H) * W + line) * C + c;
+        float2 wt[K][2];
+#pragma unroll
+        for (int t = 0; t < K; ++t) {
+            float f[4];
+            V::unpack(__ldg(reinterpret_cast<const Raw*>(w + (size_t)t * C + c)), f);
+            wt[t][0] = make_float2(f[0], f[1]); wt[t][1] = make_float2(f[2], f[3]);
+        }
+        float2 bz0 = make_float2(0.f, 0.f), bz1 = bz0;
+        if (bias) { const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c)); bz0 = make_float2(b4.x, b4.y); bz1 = make_float2(b4.z, b4.w); }
+        float2 acc[kSR][2];                                   // accumulators start at the bias
+#pragma unroll
+        for (int o = 0; o < kSR; ++o) { acc[o][0] = bz0; acc[o][1] = bz1; }
+#pragma unroll
+        for (int i = 0; i < kSR + K - 1; ++i) {
+            const int s = s0 - P + i;
+            float xv[4];
+            Raw raw = V::zero();
+            if (s >= 0 && s < L) raw = __ldg(reinterpret_cast<const Raw*>(x + base + (size_t)s * step));
+            V::unpack(raw, xv);
+            const float2 x0 = make_float2(xv[0], xv[1]), x1 = make_float2(xv[2], xv[3]);
+#pragma unroll
+            for (int o = 0; o < kSR; ++o) {
+                if (i - o >= 0 && i - o < K) {
+                    acc[o][0] = ffma2(x0, wt[i - o][0], acc[o][0]);
+                    acc[o][1] = ffma2(x1, wt[i - o][1], acc[o][1]);
+                }
+            }
+        }
+        const int p2 = (EXTRAS && res) ? min(H, res_p) : 0;
+#pragma unroll
+        for (int o = 0; o < kSR; ++o) {
+            const int s = s0 + o;
+            if (s >= L) break;
+            const int ho = ALONG_W ? line : s;
+            float a[4] = {acc[o][0].x, acc[o][0].y, acc[o][1].x, acc[o][1].y};
+            if (EXTRAS && res) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    a[q] = V::round(a[q]);
+                    if (ho < p2) a[q] += __ldg(res + (size_t)(c + q) * res_p + ho);
+                    a[q] = V::round(a[q]);
+                    if (ho >= H - p2) a[q] += __ldg(res + ((size_t)C + c + q) * res_p + (res_p - (H - ho)));
+                }
+            }
+            const size_t off = base + (size_t)s * step;
+            if (EXTRAS && add) {
+                float av[4];
+                V::unpack(*reinterpret_cast<const Raw*>(add + off), av);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) a[q] = V::round(a[q]) + av[q];
+            }
+            *reinterpret_cast<Raw*>(y + off) = V::pack(a);
+        }
+    }
+}
+
+template <typename T, int K, bool ALONG_W>
+static int dw_strip_launch_t(const void* x, const void* w, const float* bias, const float* res, int res_p, const void* add, void* y,
+                             int B, int H, int W, int C, cudaStream_t st) {
+    constexpr int kSR = StripRun<K>::value;
+    const int L = ALONG_W ? W : H, lines = ALONG_W ? H : W;
+    const long long nitems = (long long)B * lines * ((L + kSR - 1) / kSR) * (C / 4);
+    if (nitems >= (1LL << 31)) return -1;                     // caller falls back to the tiled kernel
+    const int grid = (int)std::min<long long>((nitems + 255) / 256, 148LL * 16);
+    if (res || add)
+        dw_strip_kernel<T, K, ALONG_W, true><<<grid, 256, 0, st>>>((const T*)x, (const T*)w, bias, res, res_p, (const T*)add, (T*)y, B, H, W, C, nitems);
+    else        // the plain conv: no border-residue / running-sum code at all (predicated-off instructions still cost issue slots)
+        dw_strip_kernel<T, K, ALONG_W, false><<<grid, 256, 0, st>>>((const T*)x, (const T*)w, bias, res, res_p, (const T*)add, (T*)y, B, H, W, C, nitems);
+    return 0;
+}
+
 template <typename T, int KH, int KW>
 static int dw_tile_launch_t(const void* x, const void* w, const float* bias, const float* res, int res_p, const void* add, void* y,
                             int B, int H, int W, int C, cudaStream_t st) {
@@ -184,6 +326,17 @@ template <typename T>
 static int dw_tile_dispatch(int kh, int kw, const void* x, const void* w, const float* bias, const float* res, int res_p, const void* add,
                             void* y, int B, int H, int W, int C, cudaStream_t st, bool* handled) {
     *handled = true;
+    if (getenv("CNA_DW_NO_STRIP") == nullptr) {      // (diagnostic switch: use the smem-tiled kernel for strips too)
+#define CNA_STRIP_CASE(KV) \
+        if (kh == 1 && kw == KV && dw_strip_launch_t<T, KV, true>(x, w, bias, res, res_p, add, y, B, H, W, C, st) == 0) return 0; \
+        if (kw == 1 && kh == KV && dw_strip_launch_t<T, KV, false>(x, w, bias, res, res_p, add, y, B, H, W, C, st) == 0) return 0
+        CNA_STRIP_CASE(3);
+        CNA_STRIP_CASE(5);
+        CNA_STRIP_CASE(7);
+        CNA_STRIP_CASE(11);
+        CNA_STRIP_CASE(21);
+#undef CNA_STRIP_CASE
+    }
 #define CNA_DW_CASE(KHV, KWV) \
     if (kh == KHV && kw == KWV) return dw_tile_launch_t<T, KHV, KWV>(x, w, bias, res, res_p, add, y, B, H, W, C, st)
     CNA_DW_CASE(5, 5);

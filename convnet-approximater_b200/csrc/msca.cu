@@ -57,6 +57,24 @@ template <> struct UnitOps<float> {
     __device__ static __forceinline__ float rnd(float v) { return v; }
 };
 
+
+// acc += v * w over the channels of one 4-byte unit.  bf16 units hold a channel pair: one packed FFMA2 (fma.rn.f32x2) does
+// both channels in a single issue slot — this kernel is instruction-issue bound, not FMA-pipe bound.
+template <int NCH>
+__device__ __forceinline__ void unit_fma(float (&acc)[NCH], const float (&v)[NCH], const float (&w)[NCH]) {
+    if constexpr (NCH == 2) {
+        float2 a = make_float2(acc[0], acc[1]), x = make_float2(v[0], v[1]), ww = make_float2(w[0], w[1]);
+        unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rx = *reinterpret_cast<unsigned long long*>(&x),
+                           rw = *reinterpret_cast<unsigned long long*>(&ww), rd;
+        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(rx), "l"(rw), "l"(ra));
+        float2 d = *reinterpret_cast<float2*>(&rd);
+        acc[0] = d.x; acc[1] = d.y;
+    } else {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) acc[c] = fmaf(v[c], w[c], acc[c]);
+    }
+}
+
 __host__ __device__ constexpr int sd_pitch(int cols) { return ((cols * SD_UNITS + 31) / 32) * 32 + 8; }  // units
 constexpr int SD_XC = SD_WT + 2 * SD_P + 4;     // 56 x columns   (strip + 10 + 2 each side)
 constexpr int SD_AC = SD_WT + 2 * SD_P;         // 52 a0 columns
@@ -98,8 +116,7 @@ __device__ __forceinline__ void sd_hpass(const uint32_t* __restrict__ A0, uint32
         for (int i = 0; i < 4; ++i) {
             const int tap = j - i;
             if (tap >= 0 && tap < K) {
-#pragma unroll
-                for (int c = 0; c < NCH; ++c) acc[i][c] = fmaf(v[c], wt[tap][c], acc[i][c]);
+                unit_fma<NCH>(acc[i], v, wt[tap]);
             }
         }
     }
@@ -137,8 +154,7 @@ __device__ __forceinline__ void sd_vpass(const uint32_t* __restrict__ Tk, const 
         for (int i = 0; i < 4; ++i) {
             const int tap = j - i;
             if (tap >= 0 && tap < K) {
-#pragma unroll
-                for (int c = 0; c < NCH; ++c) acc[i][c] = fmaf(v[c], wt[tap][c], acc[i][c]);
+                unit_fma<NCH>(acc[i], v, wt[tap]);
             }
         }
     }
@@ -250,8 +266,7 @@ msca_sd_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restri
                         for (int i = 0; i < 7; ++i) {
                             const int tap = j - i;
                             if (tap >= 0 && tap < 5) {
-#pragma unroll
-                                for (int c = 0; c < NCH; ++c) acc[i][c] = fmaf(v[c], wt[tap][c], acc[i][c]);
+                                unit_fma<NCH>(acc[i], v, wt[tap]);
                             }
                         }
                     }

@@ -35,6 +35,10 @@ _SIGS = {
     "cna_lowrank2_pack": "ppppiiiiiip",
     "cna_lowrank2_fused_forward": "pppppiiiiiiiiip",
     "cna_lowrank2_fused_supported": "iiiiii",
+    "cna_lowrank2_fused_forward_t": "ppppppiiiiiiiip",
+    "cna_tapconv3_tc_forward": "pppiiiiiip",
+    "cna_wgrad3_tc": "pppiiiiiiiiip",
+    "cna_bias_grad": "ppLiip",
     "cna_lowrank2_fused_forward_traced": "pppppiiiiiiiippi",
     "cna_maxpool2x2": "ppiiiiip",
     "cna_msca_sd_supported": "iiipi",
@@ -357,6 +361,55 @@ def lowrank2_fused_traced(x, wv, wh, bias, tiles=32, relu=False):
         _check(lib().cna_lowrank2_fused_forward_traced(_p(x), _p(wv), _p(wh), _p(bias), _p(y), Bn, H, W, cp, kp, N, d,
                                                        int(relu), _stream(x), _p(trace), tiles))
     return y, trace
+
+
+def lowrank2_fused_with_t(x, wv, wh, bias, relu=False):
+    """Like lowrank2_fused, also returning the bf16 intermediate T = v_conv(x), (B,H,W,k_pad), written by the same kernel."""
+    _ready(x)
+    B, H, W, cp = x.shape
+    d, kp, cp2 = wv.shape
+    N = wh.shape[1]
+    assert cp == cp2 and x.dtype == torch.bfloat16 and x.is_contiguous()
+    y = torch.empty((B, H, W, N), device=x.device, dtype=torch.bfloat16)
+    t = torch.empty((B, H, W, kp), device=x.device, dtype=torch.bfloat16)
+    with torch.cuda.device(x.device):
+        _check(lib().cna_lowrank2_fused_forward_t(_p(x), _p(wv), _p(wh), _p(bias), _p(y), _p(t), B, H, W, cp, kp, N, d, int(relu), _stream(x)))
+    return y, t
+
+
+def tapconv3_tc(x, w_packed, axis):
+    """3-tap 'same' conv on tcgen05: x (B,H,W,c_pad) bf16, w_packed [3][k_pad][c_pad] bf16 -> (B,H,W,k_pad) bf16; taps along H (axis 0) or W (1)."""
+    _ready(x)
+    B, H, W, cp = x.shape
+    d, kp, cp2 = w_packed.shape
+    assert d == 3 and cp == cp2 and x.dtype == torch.bfloat16 and x.is_contiguous() and w_packed.dtype == torch.bfloat16
+    out = torch.empty((B, H, W, kp), device=x.device, dtype=torch.bfloat16)
+    with torch.cuda.device(x.device):
+        _check(lib().cna_tapconv3_tc_forward(_p(x), _p(w_packed), _p(out), B, H, W, cp, kp, int(axis), _stream(x)))
+    return out
+
+
+def wgrad3_tc(a, bm, dw, Ca, kb, axis, wide_is_input):
+    """Writes the 3-tap conv weight gradient into fp32 `dw` (reference OIHW layout) on tcgen05.
+    a (B,H,W,ca_stride) bf16 = the wide tensor (x or dL/dy), bm (B,H,W,kb_stride<=64) bf16 = the narrow one (dL/dT or T)."""
+    _ready(a)
+    B, H, W, cs = a.shape
+    ks = bm.shape[3]
+    assert bm.shape[:3] == a.shape[:3] and a.dtype == bm.dtype == torch.bfloat16 and a.is_contiguous() and bm.is_contiguous()
+    assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == Ca * kb * 3
+    with torch.cuda.device(a.device):
+        _check(lib().cna_wgrad3_tc(_p(a), _p(bm), _p(dw), B, H, W, cs, int(Ca), ks, int(kb), int(axis), int(wide_is_input), _stream(a)))
+    return dw
+
+
+def bias_grad(g, db):
+    """db[n] = sum over pixels of g (B,H,W,N) NHWC; db fp32 (N,), overwritten."""
+    _ready(g)
+    N = g.shape[3]
+    assert g.is_contiguous() and db.dtype == torch.float32 and db.numel() == N
+    with torch.cuda.device(g.device):
+        _check(lib().cna_bias_grad(_p(g), _p(db), g.numel() // N, N, dtype_code(g.dtype), _stream(g)))
+    return db
 
 
 def lowrank2_fused(x, wv, wh, bias, relu=False, pool=False):

@@ -60,10 +60,27 @@ class Scheme2Reconstructor:
         L = self.layer
         Bn = x.shape[0]
         gb = Bn * self.world if global_batch is None else global_batch
+        dv, dh, db = self._views(self.grad)
+        C, K, N = L.in_channels, L.num_base, L.out_channels
+        _, H, W, cx = x.shape
+        if L._fusable(x.dtype, H, W) and cx == B.round_up(C, 16) and L.kernel_size == (3, 3):
+            # tensor-core path: the forward writes T = v_conv(x) next to y; both weight gradients and the data gradient
+            # through h_conv are tcgen05 kernels fed straight from the NHWC tensors
+            wv, wh = _ops.cached(L, "lr2_pack", (L.v_conv.weight, L.h_conv.weight), torch.bfloat16,
+                                 lambda: B.lowrank2_pack(L.v_conv.weight, L.h_conv.weight))
+            y, t = B.lowrank2_fused_with_t(x, wv, wh, _ops.bias_f32(L.h_conv))
+            norms, g = B.l2_recon(y, y_old.contiguous(), self.l2_weight / gb)
+            B.wgrad3_tc(g, t, dh, N, K, 1, 0)                               # dL/dWh[n][k][t]
+            B.bias_grad(g, db)
+            # dL/dT = g convolved along W with h_conv's flipped, transposed taps: a (K, N, 3, 1) "v_conv" weight
+            wd = _ops.cached(L.h_conv, "lr2_dgrad_pack", (L.h_conv.weight,), torch.bfloat16,
+                             lambda: B.lowrank2_pack(L.h_conv.weight.detach().permute(1, 0, 3, 2).flip(2).contiguous(),
+                                                     torch.zeros(64, K, 1, 3, device=x.device))[0])
+            gt = B.tapconv3_tc(g, wd, 1)
+            B.wgrad3_tc(x, gt, dv, C, K, 0, 1)                              # dL/dWv[k][c][t]
+            return norms
         y = L.forward_nhwc(x)
         norms, g = B.l2_recon(y, y_old.contiguous(), self.l2_weight / gb)
-        dv, dh, db = self._views(self.grad)
-        C = L.in_channels
         xg = x if x.shape[3] == C else x[..., :C].contiguous()
         t = _ops.dense_taps(L.v_conv, xg)                                    # T recomputed: never stored by the fused forward
         B.conv_taps_wgrad(t, g, L.kernel_size[1], 1, L.padding[1], dw_out=dh, db_out=db)

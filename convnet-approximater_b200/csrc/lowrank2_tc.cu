@@ -73,6 +73,11 @@ struct LR2Params {
     uint32_t off_y;               // y staging (2 x kYBuf, one per epilogue group)
     uint32_t off_p;               // pooled staging (2 x 4 KB), only when pool
     uint32_t off_bias, off_bar;
+    // optional: the T-epilogue also writes bf16 T = v_conv(x) to global memory (element strides: image, tile-row axis, tile-col
+    // axis); t_only = 1 skips GEMM2 and the y path altogether (a plain 3-tap C -> KP convolution along the tile-row axis)
+    __nv_bfloat16* t_out;
+    long long t_sb, t_sr, t_sc;
+    int t_only;
     int debug;             // diagnostic bit mask (CNA_LR2_DEBUG): 1 skip y TMA store, 2 skip y staging stores, 16 load x only once, 32 skip A copies, 64 skip Y TMEM load, 128 skip GEMM1 MMAs
     long long* trace;      // diagnostic: per-tile clock64() stamps of CTA 0 (NULL = off), kTraceEv slots per tile
     int trace_tiles, trace_skip;
@@ -198,10 +203,10 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             constexpr uint32_t v_bytes = 3 * KP * XROW;
             constexpr uint32_t h_bytes = NT2 * HROW;
             if (p.resident && elect_one()) {
-                mbar_arrive_expect_tx(bar(BAR_WFULL), v_bytes * p.nch + h_bytes * 3 * p.nn2);
+                mbar_arrive_expect_tx(bar(BAR_WFULL), v_bytes * p.nch + (p.t_only ? 0u : h_bytes * 3 * p.nn2));
                 for (int ch = 0; ch < p.nch; ++ch)
                     tma_load_2d(base + p.off_v + ch * p.v_chunk, &tm_wv, bar(BAR_WFULL), ch * CK, 0);
-                for (int n2 = 0; n2 < p.nn2; ++n2)
+                for (int n2 = 0; n2 < (p.t_only ? 0 : p.nn2); ++n2)
                     for (int dx = 0; dx < 3; ++dx)
                         tma_load_2d(base + p.off_h + (n2 * 3 + dx) * p.h_slot, &tm_wh, bar(BAR_WFULL), 0, dx * p.N + n2 * NT2);
             }
@@ -224,7 +229,7 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 if (lane == 0) stamp(it, 0);
             }
         }
-    } else if (warp == 15 && !p.resident) {
+    } else if (warp == 15 && !p.resident && !p.t_only) {
         // =========================== Wh TMA producer (streamed weights only) ===========================
         if (my_tiles > 0) {
             constexpr uint32_t h_bytes = NT2 * HROW;
@@ -282,6 +287,8 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 if (lane == 0) stamp(it, 3);
             }
         }
+    } else if (p.t_only && (warp == 10 || warp == 15)) {
+        // 3-tap convolution only: no GEMM2
     } else if (warp == 10 || (warp == 15 && p.resident && p.nn2 == 1)) {
         // =========================== GEMM2 issuer (A = bf16 T in TMEM, B = Wh tap slot in smem) ===========================
         // With resident weights and a single N-tile per tile (the 64-channel layers) the even and the odd tiles form two
@@ -379,6 +386,17 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             uint32_t pk[ACOLS];                               // column c holds k = 2c (low half) and 2c+1 (high half)
 #pragma unroll
             for (int c = 0; c < ACOLS; ++c) pk[c] = pack_bf16(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]));
+            if (p.t_out != nullptr) {
+                const TileCoord t = decode_tile(first + it * step, p);
+                const int m = lg * 32 + lane, r = m >> 4, xc = m & 15;
+                const int h = t.h0 + r, w = t.w0 + xc - 1;
+                if (xc >= 1 && xc <= kValidCols && h < p.H && w < p.W) {
+                    uint4* dst = reinterpret_cast<uint4*>(p.t_out + (long long)t.b * p.t_sb + (long long)h * p.t_sr + (long long)w * p.t_sc);
+#pragma unroll
+                    for (int c4 = 0; c4 < ACOLS / 4; ++c4) dst[c4] = make_uint4(pk[c4 * 4], pk[c4 * 4 + 1], pk[c4 * 4 + 2], pk[c4 * 4 + 3]);
+                }
+            }
+            if (!p.t_only) {
             // the A buffer must have been read: by GEMM2 of tile it-2 (two buffers) or of tile it-1 (one, the other group's)
             if (NABUF == 2) mbar_wait(bar(BAR_TA_EMPTY + tg), ph ^ 1u);
             else if (it > 0) mbar_wait(bar(BAR_TA_EMPTY + (tg ^ 1)), (uint32_t)(((it - 1) >> 1) & 1));
@@ -401,6 +419,7 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             tmem_st_wait();
             tc_fence_before_sync();
             mbar_arrive(bar(BAR_TA_FULL + tg));
+            }
             if (stamper) stamp(it, 7);
         }
     } else if (warp == 15) {
@@ -425,7 +444,7 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         const float lo = p.relu ? 0.f : -INFINITY;
         const uint32_t sb = base + p.off_y + g * kYBuf;
         const uint32_t pb = base + p.off_p + g * 4096;
-        const int nq = my_tiles * p.nn2;
+        const int nq = p.t_only ? 0 : my_tiles * p.nn2;
         const int q0 = NT2 == 64 ? g : 0, qstep = NT2 == 64 ? 2 : 1;
         int j = 0, n2 = q0;                      // q = j * nn2 + n2
         while (n2 >= p.nn2 && j < my_tiles) { n2 -= p.nn2; ++j; }
@@ -669,11 +688,15 @@ static int lr2_launch_kp(int KP, int NT2, int grid, size_t smem, int max_smem, c
     return lr2_launch_nt<CKV, 64>(NT2, grid, smem, max_smem, st, tm_x, tm_wv, tm_wh, tm_y, bias, p);
 }
 
-static int lr2_launch(const void* x, const void* wv_packed, const void* wh_packed, const float* bias, void* y,
-                      int B, int H, int W, int c_pad, int k_pad, int N, int d, int relu, int pool, void* stream,
+// axis: 0 = vertical taps run along the image H axis (the normal forward), 1 = along W (the image is presented to the kernel
+// transposed through the tensor maps' strides; only available in t_only mode).  H, W are the IMAGE dims.
+static int lr2_launch(const void* x, const void* wv_packed, const void* wh_packed, const float* bias, void* y, void* t_out, int t_only,
+                      int axis, int B, int H, int W, int c_pad, int k_pad, int N, int d, int relu, int pool, void* stream,
                       long long* trace, int trace_tiles) {
-    CNA_CHECK(x && wv_packed && wh_packed && y, "null pointer");
+    CNA_CHECK(x && wv_packed && (t_only || (wh_packed && y)) && (!t_only || t_out), "null pointer");
     CNA_CHECK(B > 0, "bad batch");
+    if (t_only) { N = 64; pool = 0; }
+    CNA_CHECK(axis == 0 || t_only, "axis 1 is only available for the 3-tap convolution");
     CNA_CHECK(shape_ok(H, W, c_pad, k_pad, N, d), "configuration not supported by the fused kernel "
               "(needs d=3, c_pad%16==0, k_pad in {16,32,64}, N%64==0)");
     static int num_sms = 0, max_smem = 0;
@@ -684,13 +707,18 @@ static int lr2_launch(const void* x, const void* wv_packed, const void* wh_packe
         CNA_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     }
     const int CK = pick_ck(c_pad), NT2 = pick_nt2(N);
+    const int KH = axis == 0 ? H : W, KW = axis == 0 ? W : H;      // dims along the kernel's tile-row / tile-col axes
     LR2Params p{};
     CNA_CHECK(!pool || (H % 2 == 0 && W % 2 == 0), "fused 2x2 max-pool needs even H and W");
-    p.B = B; p.H = H; p.W = W; p.N = N; p.relu = relu; p.pool = pool ? 1 : 0; p.trace = trace; p.trace_tiles = trace_tiles;
+    p.B = B; p.H = KH; p.W = KW; p.N = N; p.relu = relu; p.pool = pool ? 1 : 0; p.trace = trace; p.trace_tiles = trace_tiles;
+    p.t_out = (__nv_bfloat16*)t_out; p.t_only = t_only ? 1 : 0;
+    p.t_sb = (long long)H * W * k_pad;
+    p.t_sr = axis == 0 ? (long long)W * k_pad : (long long)k_pad;
+    p.t_sc = axis == 0 ? (long long)k_pad : (long long)W * k_pad;
     { const char* dbg = getenv("CNA_LR2_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
     { const char* sk = getenv("CNA_LR2_TRACE_SKIP"); p.trace_skip = sk ? atoi(sk) : 0; }
     p.nch = c_pad / CK; p.nn2 = N / NT2;
-    p.tiles_w = ceil_div(W, kValidCols); p.tiles_h = ceil_div(H, kTileRows);
+    p.tiles_w = ceil_div(KW, kValidCols); p.tiles_h = ceil_div(KH, kTileRows);
     long long ntiles = (long long)B * p.tiles_w * p.tiles_h;
     CNA_CHECK(ntiles < (1LL << 31), "too many tiles for one launch");
     p.ntiles = (int)ntiles;
@@ -699,8 +727,10 @@ static int lr2_launch(const void* x, const void* wv_packed, const void* wh_packe
 
     CUtensorMap tm_x, tm_wv, tm_wh, tm_y;
     {
-        cuuint64_t dims[4] = {(cuuint64_t)c_pad, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-        cuuint64_t str[3] = {(cuuint64_t)c_pad * 2, (cuuint64_t)W * c_pad * 2, (cuuint64_t)H * W * c_pad * 2};
+        // dims (channels, tile-col axis, tile-row axis, image)
+        const cuuint64_t s_h = (cuuint64_t)W * c_pad * 2, s_w = (cuuint64_t)c_pad * 2;
+        cuuint64_t dims[4] = {(cuuint64_t)c_pad, (cuuint64_t)KW, (cuuint64_t)KH, (cuuint64_t)B};
+        cuuint64_t str[3] = {axis == 0 ? s_w : s_h, axis == 0 ? s_h : s_w, (cuuint64_t)H * W * c_pad * 2};
         cuuint32_t box[4] = {(cuuint32_t)CK, kTileCols, kXRows, 1};
         if (encode(&tm_x, x, 4, dims, str, box, swizzle_for(CK * 2))) return 1;
     }
@@ -710,13 +740,15 @@ static int lr2_launch(const void* x, const void* wv_packed, const void* wh_packe
         cuuint32_t box[2] = {(cuuint32_t)CK, (cuuint32_t)(3 * k_pad)};
         if (encode(&tm_wv, wv_packed, 2, dims, str, box, swizzle_for(CK * 2))) return 1;
     }
-    {
-        cuuint64_t dims[2] = {(cuuint64_t)k_pad, (cuuint64_t)3 * N};
-        cuuint64_t str[1] = {(cuuint64_t)k_pad * 2};
-        cuuint32_t box[2] = {(cuuint32_t)k_pad, (cuuint32_t)NT2};
-        if (encode(&tm_wh, wh_packed, 2, dims, str, box, swizzle_for(k_pad * 2))) return 1;
-    }
-    {
+    if (t_only) {
+        tm_wh = tm_wv; tm_y = tm_x;        // never dereferenced in this mode
+    } else {
+        {
+            cuuint64_t dims[2] = {(cuuint64_t)k_pad, (cuuint64_t)3 * N};
+            cuuint64_t str[1] = {(cuuint64_t)k_pad * 2};
+            cuuint32_t box[2] = {(cuuint32_t)k_pad, (cuuint32_t)NT2};
+            if (encode(&tm_wh, wh_packed, 2, dims, str, box, swizzle_for(k_pad * 2))) return 1;
+        }
         const int Wy = pool ? W / 2 : W, Hy = pool ? H / 2 : H;
         cuuint64_t dims[4] = {(cuuint64_t)N, (cuuint64_t)Wy, (cuuint64_t)Hy, (cuuint64_t)B};
         cuuint64_t str[3] = {(cuuint64_t)N * 2, (cuuint64_t)Wy * N * 2, (cuuint64_t)Hy * Wy * N * 2};
@@ -758,13 +790,25 @@ int cna_lowrank2_pack(const float* v_w, const float* h_w, void* wv_packed, void*
 
 int cna_lowrank2_fused_forward(const void* x, const void* wv_packed, const void* wh_packed, const float* bias, void* y,
                                int B, int H, int W, int c_pad, int k_pad, int N, int d, int relu, int pool, void* stream) {
-    return lr2_launch(x, wv_packed, wh_packed, bias, y, B, H, W, c_pad, k_pad, N, d, relu, pool, stream, nullptr, 0);
+    return lr2_launch(x, wv_packed, wh_packed, bias, y, nullptr, 0, 0, B, H, W, c_pad, k_pad, N, d, relu, pool, stream, nullptr, 0);
+}
+
+int cna_lowrank2_fused_forward_t(const void* x, const void* wv_packed, const void* wh_packed, const float* bias, void* y, void* t_out,
+                                 int B, int H, int W, int c_pad, int k_pad, int N, int d, int relu, void* stream) {
+    CNA_CHECK(t_out != nullptr, "null pointer");
+    return lr2_launch(x, wv_packed, wh_packed, bias, y, t_out, 0, 0, B, H, W, c_pad, k_pad, N, d, relu, 0, stream, nullptr, 0);
+}
+
+int cna_tapconv3_tc_forward(const void* x, const void* w_packed, void* out, int B, int H, int W, int c_pad, int k_pad, int axis,
+                            void* stream) {
+    CNA_CHECK(axis == 0 || axis == 1, "axis must be 0 (taps along H) or 1 (along W)");
+    return lr2_launch(x, w_packed, nullptr, nullptr, nullptr, out, 1, axis, B, H, W, c_pad, k_pad, 64, 3, 0, 0, stream, nullptr, 0);
 }
 
 int cna_lowrank2_fused_forward_traced(const void* x, const void* wv_packed, const void* wh_packed, const float* bias, void* y,
                                       int B, int H, int W, int c_pad, int k_pad, int N, int d, int relu, void* stream,
                                       long long* trace, int trace_tiles) {
-    return lr2_launch(x, wv_packed, wh_packed, bias, y, B, H, W, c_pad, k_pad, N, d, relu, 0, stream, trace, trace_tiles);
+    return lr2_launch(x, wv_packed, wh_packed, bias, y, nullptr, 0, 0, B, H, W, c_pad, k_pad, N, d, relu, 0, stream, trace, trace_tiles);
 }
 
 }  // extern "C"

@@ -203,6 +203,19 @@ int cna_conv_taps_wgrad(const void* x, const void* g, float* dw, float* dbias, i
     return 0;
 }
 
+int cna_bias_grad(const void* g, float* dbias, long long P, int N, int dtype, void* stream) {
+    CNA_CHECK(g && dbias && P > 0 && N > 0, "bad arguments");
+    cudaStream_t st = as_stream(stream);
+    CNA_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * N, st));
+    int ppc = (int)std::max<long long>(64, ceil_div_ll(P, 148 * 4));
+    int grid_b = (int)ceil_div_ll(P, ppc);
+    if (dtype == CNA_F32) bias_grad_kernel<float><<<grid_b, 256, 0, st>>>((const float*)g, dbias, P, N, ppc);
+    else if (dtype == CNA_BF16) bias_grad_kernel<__nv_bfloat16><<<grid_b, 256, 0, st>>>((const __nv_bfloat16*)g, dbias, P, N, ppc);
+    else CNA_FAIL("unsupported dtype");
+    CNA_LAUNCH_OK();
+    return 0;
+}
+
 int cna_pack_taps_weight_dgrad(const float* w_oit, void* packed, int O, int I, int taps, int dtype, void* stream) {
     CNA_CHECK(w_oit && packed && O > 0 && I > 0 && taps > 0, "bad arguments");
     long long total = (long long)taps * O * I;

@@ -109,6 +109,16 @@ int cna_lowrank2_pack(const float* v_w /*(K,C,d,1)*/, const float* h_w /*(N,K,1,
 int cna_lowrank2_fused_forward(const void* x, const void* wv_packed, const void* wh_packed, const float* bias,
                                void* y, int B, int H, int W, int c_pad, int k_pad, int N, int d,
                                int relu, int pool, void* stream);
+/* Same as cna_lowrank2_fused_forward (no pool), additionally writing the bf16 intermediate T = v_conv(x), [B, H, W, k_pad], from the
+ * kernel's T-epilogue: the reconstruction step needs T for h_conv's weight gradient and gets it without a second pass over x. */
+int cna_lowrank2_fused_forward_t(const void* x, const void* wv_packed, const void* wh_packed, const float* bias, void* y, void* t_out,
+                                 int B, int H, int W, int c_pad, int k_pad, int N, int d, int relu, void* stream);
+/* 3-tap 'same' convolution C -> K <= 64 on tcgen05 (the fused kernel's GEMM1 alone): out[B,H,W,k_pad] bf16, taps along H (axis 0,
+ * = v_conv) or along W (axis 1, = the data gradient through h_conv when w_packed holds its flipped, transposed taps).
+ * w_packed [3][k_pad][c_pad] bf16 as produced by cna_lowrank2_pack for a (K, C, 3, 1) weight.
+ * Replaces autograd's conv backward-data for h_conv and the v_conv recompute (src/approx/hooks/finetune.py:329-330). */
+int cna_tapconv3_tc_forward(const void* x, const void* w_packed, void* out, int B, int H, int W, int c_pad, int k_pad, int axis,
+                            void* stream);
 /* Diagnostic variant: CTA 0 additionally records clock64() stamps, 20 per tile for its first `trace_tiles` tiles
  * (`trace` holds trace_tiles + 1 rows of 20; the last row = {clock64, globaltimer} at CTA 0's start and end)
  * (0 x issued, 1 GEMM1 turn, 2 x landed, 3 GEMM1 issued, 4 GEMM2 turn, 5 T ready, 6 T-epilogue start, 7 T stored,
@@ -166,6 +176,17 @@ int cna_l2_recon_loss_grad(const void* y_new, const void* y_old, float* sumsq_sc
  * Replaces autograd's conv backward-filter for v_conv / h_conv / 1x1 convs (src/approx/hooks/finetune.py:330). */
 int cna_conv_taps_wgrad(const void* x, const void* g, float* dw, float* dbias, int B, int H, int W, int C, int N,
                         int taps, int axis, int pad, int dtype, void* stream);
+/* Weight gradient of a 3-tap 'same' convolution on tcgen05 (bf16 NHWC operands, fp32 result, dw overwritten):
+ *   wide_is_input = 1 (v_conv):  dw[k][c][t] = sum_p a[p + (t-1) e_axis][c] * bm[p][k]   a = x  [B,H,W,ca_stride], bm = dL/dT [B,H,W,kb_stride]
+ *   wide_is_input = 0 (h_conv):  dw[n][k][t] = sum_p bm[p + (t-1) e_axis][k] * a[p][n]   a = dL/dy [B,H,W,ca_stride], bm = T [B,H,W,kb_stride]
+ * in the reference's (O, I, 3, 1) / (O, I, 1, 3) layouts with I resp. O = Ca real wide channels and kb real narrow channels (<= 64).
+ * The reduction over pixels runs on the tensor cores with both operands MN-major straight from the NHWC tensors.
+ * Replaces autograd's conv backward-filter for v_conv / h_conv (src/approx/hooks/finetune.py:330); cna_conv_taps_wgrad is the
+ * fp32 / any-shape path. */
+int cna_wgrad3_tc(const void* a, const void* bm, float* dw, int B, int H, int W, int ca_stride, int Ca, int kb_stride, int kb, int axis,
+                  int wide_is_input, void* stream);
+/* dbias[n] = sum_p g[p][n] over P pixels (fp32, overwritten): the bias gradient of any conv whose output gradient is g. */
+int cna_bias_grad(const void* g, float* dbias, long long P, int N, int dtype, void* stream);
 /* Packs w[o][i][t] for the INPUT gradient of a tap conv: packed[taps-1-t][o][i]; feed to cna_conv_taps_forward with
  * C=O, N=I, pad = taps-1-pad to get dL/dx from dL/dy. */
 int cna_pack_taps_weight_dgrad(const float* w_oit, void* packed, int O, int I, int taps, int dtype, void* stream);

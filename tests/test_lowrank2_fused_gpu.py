@@ -128,3 +128,36 @@ def test_vgg_trunk_matches_oracle_small():
     y = trunk.cuda()(x.cuda())
     assert y.shape == ref.shape == (2, 512, 1, 1)
     assert O.compare4d(ref.float(), y.float().cpu()) < 2e-2      # 13 chained bf16 layers: rounding differences compound
+
+
+@pytest.mark.parametrize("case", [(2, 64, 20, 30, 64, 64), (1, 128, 9, 17, 32, 128), (2, 16, 28, 28, 16, 64)])
+def test_fused_forward_also_writes_T(case):
+    """cna_lowrank2_fused_forward_t: y identical to the plain fused call, T == v_conv(x) rounded to bf16."""
+    import torch.nn.functional as F
+    from approx import backend as B
+    Bn, C, H, W, K, N = case
+    v_w, h_w, b = make(C, K, N, 5)
+    x = torch.randn(Bn, C, H, W, generator=torch.Generator().manual_seed(3)).bfloat16()
+    wv, wh = B.lowrank2_pack(v_w.cuda().float(), h_w.cuda().float())
+    xn = B.to_nhwc(x.cuda(), B.round_up(C, 16))
+    y0 = B.lowrank2_fused(xn, wv, wh, b.float().cuda())
+    y1, t = B.lowrank2_fused_with_t(xn, wv, wh, b.float().cuda())
+    assert torch.equal(y0, y1)
+    t_ref = F.conv2d(x, v_w, None, 1, (1, 0))
+    assert O.compare4d(t_ref.float(), t[..., :K].permute(0, 3, 1, 2).float().cpu()) < 1e-3
+
+
+@pytest.mark.parametrize("axis", [0, 1])
+@pytest.mark.parametrize("case", [(2, 64, 20, 30, 64), (1, 256, 9, 17, 64), (2, 128, 28, 14, 32)])
+def test_tapconv3_tcgen05(case, axis):
+    """3-tap C -> K conv on tcgen05 along H (axis 0) and along W (axis 1, transposed tensor maps) vs torch bf16."""
+    import torch.nn.functional as F
+    from approx import backend as B
+    Bn, C, H, W, K = case
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(Bn, C, H, W, generator=g).bfloat16()
+    w = (torch.randn(K, C, 3, 1, generator=g) / (3 * C) ** 0.5).bfloat16()
+    ref = F.conv2d(x, w if axis == 0 else w.permute(0, 1, 3, 2), None, 1, (1, 0) if axis == 0 else (0, 1))
+    wv, _ = B.lowrank2_pack(w.cuda().float(), torch.zeros(64, K, 1, 3, device="cuda"))
+    out = B.tapconv3_tc(B.to_nhwc(x.cuda()).contiguous(), wv, axis)
+    assert O.compare4d(ref.float(), out[..., :K].permute(0, 3, 1, 2).float().cpu()) < 1e-3

@@ -174,3 +174,33 @@ def test_svd_topk_and_scheme2_fit():
         assert O.compare4d(ref, y.detach().cpu()) < 2e-5
         if K == 18:
             assert O.compare4d(src(x).detach(), y.detach().cpu()) < 2e-5
+
+
+@pytest.mark.parametrize("case", [(2, 64, 20, 30, 64), (1, 256, 9, 17, 64), (2, 128, 28, 14, 32), (1, 512, 14, 14, 64)])
+def test_wgrad3_tcgen05_matches_autograd(case):
+    """tcgen05 weight gradients of v_conv (taps along H, wide = input) and h_conv (taps along W, wide = output gradient)
+    against torch autograd on the same bf16 tensors (fp32 accumulation on both sides)."""
+    import torch.nn.functional as F
+    from approx import backend as B
+    from oracle import approx_oracle as O
+    Bn, C, H, W, K = case
+    g = torch.Generator().manual_seed(23)
+    x = torch.randn(Bn, C, H, W, generator=g).bfloat16()
+    gt = torch.randn(Bn, K, H, W, generator=g).bfloat16()
+    kp = 16 if K <= 16 else 32 if K <= 32 else 64
+    # v_conv: dw[k][c][t] = sum x[h+t-1] * gt[h]
+    wv = torch.zeros(K, C, 3, 1, requires_grad=True)
+    F.conv2d(x.float(), wv, None, 1, (1, 0)).backward(gt.float())
+    xn = B.to_nhwc(x.cuda()).contiguous()
+    gtn = B.to_nhwc(gt.cuda(), kp).contiguous()
+    dv = torch.zeros(K, C, 3, 1, device="cuda")
+    B.wgrad3_tc(xn, gtn, dv, C, K, 0, 1)
+    err = (dv.cpu() - wv.grad).norm() / wv.grad.norm()
+    assert err < 2e-3, err
+    # h_conv: N = C wide output channels, T narrow: dw[n][k][t] = sum T[w+t-1][k] * g[w][n]
+    wh = torch.zeros(C, K, 1, 3, requires_grad=True)
+    F.conv2d(gt.float(), wh, None, 1, (0, 1)).backward(x.float())
+    dh = torch.zeros(C, K, 1, 3, device="cuda")
+    B.wgrad3_tc(xn, gtn, dh, C, K, 1, 0)
+    err = (dh.cpu() - wh.grad).norm() / wh.grad.norm()
+    assert err < 2e-3, err

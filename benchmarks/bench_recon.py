@@ -37,6 +37,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--layers", default="conv2_1,conv3_2,conv4_2")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--weak", action="store_true", help="weak scaling: --global-batch images PER GPU (global batch = that x world size)")
+    ap.add_argument("--graph", action="store_true", help="capture the step in a CUDA graph and replay it (no host work per step)")
     args = ap.parse_args()
     from approx import backend as B
     from approx.layers import LowRankExpConvV2
@@ -50,6 +52,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     dt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    if args.weak:
+        args.global_batch *= world
     lo, hi = shard_range(args.global_batch, rank, world)
     total_ms = 0.0
     for name in args.layers.split(","):
@@ -62,8 +66,12 @@ def main():
         x = torch.randn(hi - lo, H, H, C, device=dev).to(dt)            # this rank's shard, NHWC, resident in HBM
         with torch.no_grad():                                            # teacher output once, outside the timed region
             y_old = teacher(x.permute(0, 3, 1, 2)).permute(0, 2, 3, 1).contiguous()
+        step = lambda: rec.step(x, y_old, args.global_batch)
+        if args.graph:
+            rec.capture(x, y_old, args.global_batch)
+            step = rec.replay
         for _ in range(args.warmup):
-            rec.step(x, y_old, args.global_batch)
+            step()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier(); torch.cuda.synchronize()
@@ -71,7 +79,7 @@ def main():
         n0 = B.launch_count()
         a.record()
         for _ in range(args.steps):
-            loss = rec.step(x, y_old, args.global_batch)
+            loss = step()
         b.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -82,14 +90,15 @@ def main():
         total_ms += ms.item()
         if rank == 0:
             print(json.dumps({"bench": "recon_step", "layer": name, "C": C, "N": N, "H": H, "rank_K": args.rank,
-                              "global_batch": args.global_batch, "n_gpus": world, "dtype": args.dtype, "ms_per_step": ms.item(),
+                              "global_batch": args.global_batch, "n_gpus": world, "dtype": args.dtype, "cuda_graph": bool(args.graph),
+                              "ms_per_step": ms.item(),
                               "images_per_s": args.global_batch / ms.item() * 1e3, "loss": float(loss),
                               "launches_per_step": (B.launch_count() - n0) / args.steps,
                               "allreduce_bytes": rec.grad.numel() * 4}))
     if rank == 0:
         print(json.dumps({"bench": "recon_total", "layers": args.layers, "n_gpus": world, "global_batch": args.global_batch,
                           "ms_per_step_sum": total_ms, "images_per_s": args.global_batch / total_ms * 1e3,
-                          "scaling": "strong"}))
+                          "scaling": "weak" if args.weak else "strong", "cuda_graph": bool(args.graph)}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -49,6 +49,7 @@ _SIGS = {
     "cna_conv_taps_wgrad": "ppppiiiiiiiiip",
     "cna_pack_taps_weight_dgrad": "ppiiiip",
     "cna_adamw_step": "ppppLfffffifp",
+    "cna_adamw_step_dev": "ppppLfffffpfp",
     "cna_lowrank1_svd_fit": "piiippp",
     "cna_msca_equiv_kernel": "pppppiipppp",
 }
@@ -400,6 +401,27 @@ def wgrad3_tc(a, bm, dw, Ca, kb, axis, wide_is_input):
     with torch.cuda.device(a.device):
         _check(lib().cna_wgrad3_tc(_p(a), _p(bm), _p(dw), B, H, W, cs, int(Ca), ks, int(kb), int(axis), int(wide_is_input), _stream(a)))
     return dw
+
+
+def adamw_step_dev_(p, g, m, v, step_dev, lr, betas, eps, wd, grad_scale=1.0):
+    """Graph-capturable fused AdamW: `step_dev` is a 1-element int32 device tensor counting the steps taken."""
+    _ready(p)
+    assert step_dev.dtype == torch.int32 and step_dev.numel() == 1
+    with torch.cuda.device(p.device):
+        _check(lib().cna_adamw_step_dev(_p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(betas[0]), float(betas[1]), float(eps),
+                                        float(wd), _p(step_dev), float(grad_scale), _stream(p)))
+    return p
+
+
+def lowrank2_pack_into(v_w, h_w, wv, wh):
+    """cna_lowrank2_pack into existing buffers (fixed addresses: what a captured CUDA graph needs)."""
+    _ready(v_w)
+    K, C, d = v_w.shape[0], v_w.shape[1], v_w.shape[2]
+    N = h_w.shape[0]
+    assert v_w.dtype == h_w.dtype == torch.float32 and v_w.is_contiguous() and h_w.is_contiguous()
+    with torch.cuda.device(v_w.device):
+        _check(lib().cna_lowrank2_pack(_p(v_w), _p(h_w), _p(wv), _p(wh), C, K, N, d, wv.shape[2], wv.shape[1], _stream(v_w)))
+    return wv, wh
 
 
 def bias_grad(g, db):

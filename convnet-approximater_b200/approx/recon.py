@@ -46,6 +46,10 @@ class Scheme2Reconstructor:
         self.exp_avg = torch.zeros(n, device=dev, dtype=torch.float32)
         self.exp_avg_sq = torch.zeros(n, device=dev, dtype=torch.float32)
         self.t = 0
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)     # device-side step counter (graph mode)
+        self._graph = None
+        self._graph_io = None
+        self._packs = None                                                 # persistent packed weights (graph mode)
 
     def _views(self, flat):
         nv, nh, nb = self.sizes
@@ -66,16 +70,25 @@ class Scheme2Reconstructor:
         if L._fusable(x.dtype, H, W) and cx == B.round_up(C, 16) and L.kernel_size == (3, 3):
             # tensor-core path: the forward writes T = v_conv(x) next to y; both weight gradients and the data gradient
             # through h_conv are tcgen05 kernels fed straight from the NHWC tensors
-            wv, wh = _ops.cached(L, "lr2_pack", (L.v_conv.weight, L.h_conv.weight), torch.bfloat16,
-                                 lambda: B.lowrank2_pack(L.v_conv.weight, L.h_conv.weight))
-            y, t = B.lowrank2_fused_with_t(x, wv, wh, _ops.bias_f32(L.h_conv))
+            if self._packs is not None:
+                # graph mode: re-pack from the fp32 master weights into fixed buffers inside the captured step
+                mv, mh, mb = self._views(self.master)
+                wv, wh, wd = self._packs
+                B.lowrank2_pack_into(mv, mh, wv, wh)
+                B.lowrank2_pack_into(mh.permute(1, 0, 2).flip(2).contiguous(), self._dummy_h, wd, self._dummy_wh)
+                bias = mb
+            else:
+                wv, wh = _ops.cached(L, "lr2_pack", (L.v_conv.weight, L.h_conv.weight), torch.bfloat16,
+                                     lambda: B.lowrank2_pack(L.v_conv.weight, L.h_conv.weight))
+                wd = _ops.cached(L.h_conv, "lr2_dgrad_pack", (L.h_conv.weight,), torch.bfloat16,
+                                 lambda: B.lowrank2_pack(L.h_conv.weight.detach().permute(1, 0, 3, 2).flip(2).contiguous(),
+                                                         torch.zeros(64, K, 1, 3, device=x.device))[0])
+                bias = _ops.bias_f32(L.h_conv)
+            y, t = B.lowrank2_fused_with_t(x, wv, wh, bias)
             norms, g = B.l2_recon(y, y_old.contiguous(), self.l2_weight / gb)
             B.wgrad3_tc(g, t, dh, N, K, 1, 0)                               # dL/dWh[n][k][t]
             B.bias_grad(g, db)
-            # dL/dT = g convolved along W with h_conv's flipped, transposed taps: a (K, N, 3, 1) "v_conv" weight
-            wd = _ops.cached(L.h_conv, "lr2_dgrad_pack", (L.h_conv.weight,), torch.bfloat16,
-                             lambda: B.lowrank2_pack(L.h_conv.weight.detach().permute(1, 0, 3, 2).flip(2).contiguous(),
-                                                     torch.zeros(64, K, 1, 3, device=x.device))[0])
+            # dL/dT = g convolved along W with h_conv's flipped, transposed taps (wd: a (K, N, 3, 1) "v_conv" weight)
             gt = B.tapconv3_tc(g, wd, 1)
             B.wgrad3_tc(x, gt, dv, C, K, 0, 1)                              # dL/dWv[k][c][t]
             return norms
@@ -94,7 +107,10 @@ class Scheme2Reconstructor:
         """All-reduce the flat gradient, AdamW on the master copy, refresh the layer's parameters."""
         allreduce_flat_(self.grad, self.group)
         self.t += 1
-        B.adamw_step_(self.master, self.grad, self.exp_avg, self.exp_avg_sq, self.t, self.lr, self.betas, self.eps, self.wd)
+        if self._packs is not None:
+            B.adamw_step_dev_(self.master, self.grad, self.exp_avg, self.exp_avg_sq, self.step_dev, self.lr, self.betas, self.eps, self.wd)
+        else:
+            B.adamw_step_(self.master, self.grad, self.exp_avg, self.exp_avg_sq, self.t, self.lr, self.betas, self.eps, self.wd)
         mv, mh, mb = self._views(self.master)
         L = self.layer
         with torch.no_grad():
@@ -107,3 +123,42 @@ class Scheme2Reconstructor:
         norms = self.gradients(x, y_old, global_batch)
         self.apply()
         return norms.mean()
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # CUDA-graph mode: the whole step (pack, fused forward + T, loss/gradient, three tcgen05 backward kernels, NCCL
+    # all-reduce, AdamW, parameter refresh) is captured once and replayed, so a step costs no host work.  At 8 GPUs a
+    # step of the tensor-core path is ~0.2 ms of kernels; ~15 launches + one collective issued from Python would
+    # otherwise dominate it.
+    # ------------------------------------------------------------------------------------------------------------------
+    def capture(self, x: torch.Tensor, y_old: torch.Tensor, global_batch: Optional[int] = None):
+        """Captures one step on static buffers `x` / `y_old` (copy new minibatches into them between replays)."""
+        L = self.layer
+        C, K, N = L.in_channels, L.num_base, L.out_channels
+        _, H, W, cx = x.shape
+        if not (L._fusable(x.dtype, H, W) and cx == B.round_up(C, 16) and L.kernel_size == (3, 3)):
+            raise NotImplementedError("graph mode covers the tensor-core path (bf16, 3x3, stride 1)")
+        dev = x.device
+        kp, cp = B.lowrank2_k_pad(K), B.round_up(C, 16)
+        self._packs = (torch.zeros(3, kp, cp, device=dev, dtype=torch.bfloat16), torch.zeros(3, N, kp, device=dev, dtype=torch.bfloat16),
+                       torch.zeros(3, kp, N, device=dev, dtype=torch.bfloat16))
+        self._dummy_h = torch.zeros(64, K, 3, device=dev)
+        self._dummy_wh = torch.zeros(3, 64, kp, device=dev, dtype=torch.bfloat16)
+        self.step_dev.fill_(self.t)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                       # warm-up off the capture: one-time attribute / cache setup
+            for _ in range(2):
+                self.step(x, y_old.contiguous(), global_batch)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._graph_loss = self.step(x, y_old, global_batch)
+        self._graph_io = (x, y_old)
+        return self._graph
+
+    def replay(self):
+        """Replays the captured step; returns the mean per-sample norm tensor of this rank (overwritten by each replay)."""
+        self._graph.replay()
+        self.t += 1
+        return self._graph_loss

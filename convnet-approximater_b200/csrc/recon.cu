@@ -121,6 +121,23 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const T* __restrict__ g,
     }
 }
 
+__global__ void __launch_bounds__(256) adamw_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                       float* __restrict__ v, long long n, float lr, float beta1, float beta2,
+                                                       float eps, float wd, const int* __restrict__ step_dev, float gscale) {
+    const float step = (float)(*step_dev + 1);
+    const float bc1 = 1.f - powf(beta1, step), bc2 = 1.f - powf(beta2, step);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float gi = g[i] * gscale;
+        float pi = p[i] * (1.f - lr * wd);
+        float mi = beta1 * m[i] + (1.f - beta1) * gi;
+        float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+        p[i] = pi - (lr / bc1) * mi / denom;
+    }
+}
+__global__ void bump_step_kernel(int* step_dev) { *step_dev += 1; }
+
 // w[o][i][t] fp32 -> packed[taps-1-t][o_pad rows = input of the transposed conv][i_pad cols = its output]
 template <typename T>
 __global__ void pack_taps_dgrad_kernel(const float* __restrict__ w, T* __restrict__ out, int O, int I, int taps) {
@@ -234,6 +251,20 @@ int cna_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_a
     int grid = (int)std::min<long long>(ceil_div_ll(n, 256), 148LL * 8);
     adamw_kernel<<<grid, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
                                                      bc1, bc2, grad_scale);
+    CNA_LAUNCH_OK();
+    return 0;
+}
+
+/* Graph-capturable AdamW: the step counter lives on the device (bias corrections are computed in the kernel from *step_dev + 1,
+ * a second one-thread kernel then increments it), so a captured reconstruction step stays correct across replays. */
+int cna_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                       float beta2, float eps, float weight_decay, int* step_dev, float grad_scale, void* stream) {
+    CNA_CHECK(param && grad && exp_avg && exp_avg_sq && step_dev && n > 0, "bad arguments");
+    int grid = (int)std::min<long long>(ceil_div_ll(n, 256), 148LL * 8);
+    adamw_dev_kernel<<<grid, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
+                                                         step_dev, grad_scale);
+    CNA_LAUNCH_OK();
+    bump_step_kernel<<<1, 1, 0, as_stream(stream)>>>(step_dev);
     CNA_LAUNCH_OK();
     return 0;
 }

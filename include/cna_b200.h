@@ -194,6 +194,10 @@ int cna_pack_taps_weight_dgrad(const float* w_oit, void* packed, int O, int I, i
  * (1/world_size after an all-reduce(SUM)).  Replaces optimizer.step() at src/approx/hooks/finetune.py:331. */
 int cna_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
                    float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+/* Same, with the step counter on the device (*step_dev holds the number of steps taken so far and is incremented): the call is
+ * CUDA-graph capturable, so a whole reconstruction step can be replayed without host work. */
+int cna_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                       float beta2, float eps, float weight_decay, int* step_dev, float grad_scale, void* stream);
 
 /* 2x2/stride-2 max pool, NHWC (VGG trunk glue between the approximated convs). */
 int cna_maxpool2x2(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream);

@@ -3,6 +3,8 @@
 Each function returns None when the fused kernel does not apply; callers then run the
 generic depthwise kernels (still CUDA, just more launches).
 """
+import os
+
 import torch
 from torch import nn
 
@@ -51,11 +53,20 @@ def parallel_forward(par, x):
 
 def conv0_sd_forward(msca, x):
     """conv0 + sd_convs of an MSCA block as one kernel, or None."""
+    mode = os.environ.get("CNA_MSCA_FUSED", "auto")
+    if mode == "0":
+        return None
     got = _branches(msca.sd_convs)
     if got is None:
         return None
     cas, identity, fix = got
     conv0 = msca.conv0
+    if mode == "auto" and len(cas) == 1 and x.dtype == torch.bfloat16 and msca.num_channel % 32 == 0:
+        # measured on B200 (profiles/r01_msca_kernels.txt): for MscaRep's single 1x21 . 21x1 cascade the three separate
+        # register-tiled / strip launches (conv0, 1x21, 21x1 + border fix) beat the marching one-pass kernel, which is
+        # instruction-issue bound at ~15 % of the FP32 peak; with three cascades the one-pass kernel still wins once the
+        # host-side cost of nine launches is counted
+        return None
     if (conv0.kernel_size != (5, 5) or conv0.stride != (1, 1) or conv0.padding != (2, 2)
             or conv0.groups != conv0.in_channels or conv0.out_channels != conv0.in_channels):
         return None

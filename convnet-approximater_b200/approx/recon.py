@@ -11,6 +11,7 @@ data/weight gradients and a fused AdamW on one flat fp32 buffer (master weights;
 are refreshed from it).  torch.distributed (NCCL) provides the single collective per step — one all-reduce of the
 flat gradient buffer, e.g. 0.79 MB for C = N = 512, K = 64.
 """
+import os
 from typing import Optional
 
 import torch
@@ -137,6 +138,9 @@ class Scheme2Reconstructor:
         _, H, W, cx = x.shape
         if not (L._fusable(x.dtype, H, W) and cx == B.round_up(C, 16) and L.kernel_size == (3, 3)):
             raise NotImplementedError("graph mode covers the tensor-core path (bf16, 3x3, stride 1)")
+        if self.world > 1 and not os.environ.get("CNA_RECON_GRAPH_MULTI"):
+            # capturing the NCCL all-reduce hung in the one 8-GPU attempt of round 1 (cause not yet investigated)
+            raise NotImplementedError("graph mode is validated single-GPU only; multi-GPU reconstruction runs eagerly")
         dev = x.device
         kp, cp = B.lowrank2_k_pad(K), B.round_up(C, 16)
         self._packs = (torch.zeros(3, kp, cp, device=dev, dtype=torch.bfloat16), torch.zeros(3, N, kp, device=dev, dtype=torch.bfloat16),

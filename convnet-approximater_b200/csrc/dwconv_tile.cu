@@ -39,6 +39,16 @@ template <> struct Pair<float> {
     static __device__ __forceinline__ float round(float a) { return a; }
 };
 
+
+// Blackwell's packed fp32 FMA (SASS FFMA2): two independent fp32 FMAs per issued instruction — the same FLOPs per FMA-pipe
+// cycle, half the issue slots, which is what an instruction-issue-bound kernel is short of.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                       rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+
 // ALONG_W = false: thread = (channel pair, column), 16 outputs down the rows (used when KH >= KW)
 // ALONG_W = true : thread = (channel pair, row),    16 outputs along the columns (1 x k strips)
 template <typename T, int KH, int KW, bool ALONG_W>
@@ -106,10 +116,7 @@ dw_tile_kernel(const T* __restrict__ x, const T* __restrict__ w /*[KH*KW][C]*/, 
                     const float2 xv = P::unpack(col[i * XW * CP]);
 #pragma unroll
                     for (int r = 0; r < kDT; ++r) {
-                        if (i - r >= 0 && i - r < KH) {
-                            acc[r].x = fmaf(xv.x, wj[i - r].x, acc[r].x);
-                            acc[r].y = fmaf(xv.y, wj[i - r].y, acc[r].y);
-                        }
+                        if (i - r >= 0 && i - r < KH) acc[r] = ffma2(xv, wj[i - r], acc[r]);
                     }
                 }
             }
@@ -124,10 +131,7 @@ dw_tile_kernel(const T* __restrict__ x, const T* __restrict__ w /*[KH*KW][C]*/, 
                     const float2 xv = P::unpack(row[j * CP]);
 #pragma unroll
                     for (int r = 0; r < kDT; ++r) {
-                        if (j - r >= 0 && j - r < KW) {
-                            acc[r].x = fmaf(xv.x, wi_[j - r].x, acc[r].x);
-                            acc[r].y = fmaf(xv.y, wi_[j - r].y, acc[r].y);
-                        }
+                        if (j - r >= 0 && j - r < KW) acc[r] = ffma2(xv, wi_[j - r], acc[r]);
                     }
                 }
             }
@@ -173,14 +177,6 @@ dw_tile_kernel(const T* __restrict__ x, const T* __restrict__ w /*[KH*KW][C]*/, 
 // ------------------------------------------------------------------------------------------------
 template <int K> struct StripRun { static constexpr int value = K <= 7 ? 16 : 8; };   // outputs per thread along the strip axis
 
-// Blackwell's packed fp32 FMA (SASS FFMA2): two independent fp32 FMAs per issued instruction — the same FLOPs per FMA-pipe
-// cycle, half the issue slots, which is what an instruction-issue-bound streaming kernel is short of.
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
-                       rc = *reinterpret_cast<unsigned long long*>(&c), rd;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-    return *reinterpret_cast<float2*>(&rd);
-}
 
 template <typename T> struct Vec4;
 template <> struct Vec4<__nv_bfloat16> {

@@ -42,6 +42,8 @@ _SIGS = {
     "cna_lowrank2_fused_forward_traced": "pppppiiiiiiiippi",
     "cna_maxpool2x2": "ppiiiiip",
     "cna_msca_sd_supported": "iiipi",
+    "cna_msca_chain_supported": "iiipi",
+    "cna_msca_chain_forward": "pppppppppppiipiiiiiip",
     "cna_msca_sd_forward": "pppppppppipiiiiiiip",
     "cna_svd_small_batched": "ppppiiip",
     "cna_svd_jacobi_large": "piiipppip",
@@ -296,6 +298,29 @@ def maxpool2x2(x):
     with torch.cuda.device(x.device):
         _check(lib().cna_maxpool2x2(_p(x), _p(y), B, H, W, C, dtype_code(x.dtype), _stream(x)))
     return y
+
+
+def msca_chain_supported(C, k1, ks, dtype) -> bool:
+    arr = (c_int * len(ks))(*[int(k) for k in ks])
+    return bool(lib().cna_msca_chain_supported(int(C), int(k1), len(ks), ctypes.cast(arr, c_void_p), dtype_code(dtype)))
+
+
+def msca_chain(x, w0, b0, w1s, b1s, w2s, b2s, ks, identity, res=None):
+    """conv0 5x5 -> per cascade (1xk, kx1 with running sum) [-> + conv0 output] [-> border fix] as one host call that enqueues the
+    register-tiled depthwise / strip kernels.  w* packed [taps][C] in x.dtype, b* fp32 (C,) or None; lists have one entry per cascade."""
+    _ready(x)
+    Bn, H, W, C = x.shape
+    nb = len(ks)
+    assert x.is_contiguous() and len(w1s) == len(w2s) == len(b1s) == len(b2s) == nb
+    a0, t, s = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    P = lambda lst: ctypes.cast((c_void_p * nb)(*[_p(v) for v in lst]), c_void_p)
+    karr = (c_int * nb)(*[int(k) for k in ks])
+    res_p = 0 if res is None else res.shape[2]
+    with torch.cuda.device(x.device):
+        _check(lib().cna_msca_chain_forward(_p(x), _p(a0), _p(t), _p(s), _p(w0), _p(b0), P(w1s), P(b1s), P(w2s), P(b2s),
+                                            ctypes.cast(karr, c_void_p), nb, int(bool(identity)), _p(res), res_p, Bn, H, W, C,
+                                            dtype_code(x.dtype), _stream(x)))
+    return s
 
 
 def msca_sd_supported(C, k1, ks, dtype):

@@ -61,12 +61,6 @@ def conv0_sd_forward(msca, x):
         return None
     cas, identity, fix = got
     conv0 = msca.conv0
-    if mode == "auto" and len(cas) == 1 and x.dtype == torch.bfloat16 and msca.num_channel % 32 == 0:
-        # measured on B200 (profiles/r01_msca_kernels.txt): for MscaRep's single 1x21 . 21x1 cascade the three separate
-        # register-tiled / strip launches (conv0, 1x21, 21x1 + border fix) beat the marching one-pass kernel, which is
-        # instruction-issue bound at ~15 % of the FP32 peak; with three cascades the one-pass kernel still wins once the
-        # host-side cost of nine launches is counted
-        return None
     if (conv0.kernel_size != (5, 5) or conv0.stride != (1, 1) or conv0.padding != (2, 2)
             or conv0.groups != conv0.in_channels or conv0.out_channels != conv0.in_channels):
         return None
@@ -77,7 +71,19 @@ def conv0_sd_forward(msca, x):
                 or c.conv2.padding != (k // 2, 0) or c.conv1.stride != (1, 1) or c.conv2.stride != (1, 1)):
             return None
         ks.append(k)
-    if not ks or not B.msca_sd_supported(msca.num_channel, 5, ks, x.dtype):
+    if not ks:
+        return None
+    if (mode == "chain" or (mode == "auto" and len(ks) == 1)) and B.msca_chain_supported(msca.num_channel, 5, ks, x.dtype):
+        # measured on B200 at batch 32 (profiles/r01_msca_kernels.txt): for MscaRep's single 1x21 . 21x1 cascade the register-tiled
+        # 5x5 + strip kernels, enqueued back to back by one C call, beat the one-pass marching kernel below (1.47 vs 1.97 ms over
+        # MSCAN-T's 13 blocks); with three cascades the marching kernel still wins at that batch size (2.53 vs 2.76 ms) — the
+        # strip launches are too small to fill the GPU — and loses at batch 256.  CNA_MSCA_FUSED=chain / 1 force either path.
+        dw_w = lambda conv: _ops.cached(conv, "dw_w", (conv.weight,), x.dtype, lambda: B.pack_dw(conv.weight, x.dtype))
+        return B.msca_chain(x.contiguous(), dw_w(conv0), _ops.bias_f32(conv0),
+                            [dw_w(c.conv1) for c in cas], [_ops.bias_f32(c.conv1) for c in cas],
+                            [dw_w(c.conv2) for c in cas], [_ops.bias_f32(c.conv2) for c in cas],
+                            ks, identity, res=None if fix is None else fix.res_f32())
+    if not B.msca_sd_supported(msca.num_channel, 5, ks, x.dtype):
         return None
     if fix is not None and fix.p != max(ks) // 2 and False:
         return None

@@ -365,3 +365,42 @@ int dw_tile_try(const void* x, const void* w_packed, const float* bias, const fl
 }
 
 }  // namespace cna
+
+using namespace cna;
+
+extern "C" {
+
+int cna_msca_chain_supported(int C, int k1, int nb, const int* ks_host, int dtype) {
+    if (C % kDC != 0 || k1 != 5 || nb < 1 || nb > 3 || (dtype != CNA_BF16 && dtype != CNA_F32)) return 0;
+    for (int i = 0; i < nb; ++i)
+        if (ks_host[i] != 3 && ks_host[i] != 5 && ks_host[i] != 7 && ks_host[i] != 11 && ks_host[i] != 21) return 0;
+    return 1;
+}
+
+int cna_msca_chain_forward(const void* x, void* a0, void* t, void* s, const void* w0, const float* b0, const void* const* w1,
+                           const float* const* b1, const void* const* w2, const float* const* b2, const int* ks_host, int nb,
+                           int identity, const float* res, int res_p, int B, int H, int W, int C, int dtype, void* stream) {
+    CNA_CHECK(x && a0 && t && s && w0 && w1 && w2 && b1 && b2 && ks_host, "null pointer");
+    CNA_CHECK(cna_msca_chain_supported(C, 5, nb, ks_host, dtype), "configuration not supported (C % 32 == 0, k1 = 5, strips in {3,5,7,11,21})");
+    cudaStream_t st = as_stream(stream);
+    bool handled = false;
+    auto run = [&](const void* in, const void* w, const float* bias, const float* rs, int rp, const void* add, void* out, int kh, int kw) -> int {
+        handled = false;
+        if (dw_tile_try(in, w, bias, rs, rp, add, out, B, H, W, C, 1, kh, kw, 1, 1, kh / 2, kw / 2, dtype, st, &handled)) return 1;
+        CNA_CHECK(handled, "no tiled kernel for this depthwise shape");
+        count_launch();
+        return 0;
+    };
+    if (run(x, w0, b0, nullptr, 0, nullptr, a0, 5, 5)) return 1;                                   // conv0
+    const bool fuse_res = res != nullptr && nb == 1 && !identity;                                 // CascadeConv + FixPaddingBias
+    for (int i = 0; i < nb; ++i) {
+        const int k = ks_host[i];
+        if (run(a0, w1[i], b1[i], nullptr, 0, nullptr, t, 1, k)) return 1;                        // 1 x k
+        if (run(t, w2[i], b2[i], fuse_res ? res : nullptr, fuse_res ? res_p : 0, i > 0 ? s : nullptr, s, k, 1)) return 1;   // k x 1 (+ running sum)
+    }
+    if (identity && cna_add(s, a0, s, (long long)B * H * W * C, dtype, stream)) return 1;         // ParallelConv's identity branch
+    if (res != nullptr && !fuse_res && cna_fix_padding_bias(s, res, B, H, W, C, res_p, dtype, stream)) return 1;
+    return 0;
+}
+
+}  // extern "C"

@@ -139,6 +139,16 @@ int cna_lowrank2_fused_supported(int H, int W, int c_pad, int k_pad, int N, int 
  * Replaces MSCA.forward's `sd_convs(conv0(x))` (src/approx/layers/msca.py:26, depth_seperable_conv.py:12-16,45-47) and
  * MscaRep's decomp>=1 forms (src/approx/core/msca_rep.py:46-55). */
 int cna_msca_sd_supported(int C, int k1, int nb, const int* ks_host, int dtype);
+/* The same chain as ONE host call that enqueues the register-tiled depthwise / strip kernels back to back (conv0 5x5 -> a0; per
+ * cascade 1xk -> t, kx1 (+ running sum) -> s; identity add; border fix), every intermediate rounded exactly where the reference
+ * materialises a tensor.  On B200 these HBM-bound launches beat the one-pass marching kernel (which is instruction-issue bound);
+ * doing the sequencing here instead of in Python removes ~20 us of host work per launch.  Weights packed [taps][C] in the tensor
+ * dtype (cna_pack_dw_weight); w1 / b1 / w2 / b2 are HOST arrays of nb device pointers (bias entries may be NULL);
+ * a0, t, s: caller-provided tensors shaped like x (s is the result).  C % 32 == 0, k1 = 5, strips in {3,5,7,11,21}. */
+int cna_msca_chain_supported(int C, int k1, int nb, const int* ks_host, int dtype);
+int cna_msca_chain_forward(const void* x, void* a0, void* t, void* s, const void* w0, const float* b0, const void* const* w1,
+                           const float* const* b1, const void* const* w2, const float* const* b2, const int* ks_host, int nb,
+                           int identity, const float* res, int res_p, int B, int H, int W, int C, int dtype, void* stream);
 int cna_msca_sd_forward(const void* x, void* y, const float* w0, const float* b0, const float* w1cat, const float* b1cat,
                         const float* w2cat, const float* b2cat, const float* res, int res_p, const int* ks_host, int nb,
                         int identity, int B, int H, int W, int C, int dtype, void* stream);

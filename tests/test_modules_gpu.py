@@ -176,10 +176,11 @@ def _oracle_msca(m, x, dt):
 
 @pytest.mark.parametrize("C,H,W", [(32, 40, 50), (16, 7, 9), (64, 33, 32), (48, 21, 70)])
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
-def test_msca_fused_sd_kernel_vs_oracle(C, H, W, dt):
+def test_msca_fused_sd_kernel_vs_oracle(C, H, W, dt, monkeypatch):
     """The fused marching kernel (conv0 -> 3 strip cascades + identity) on ragged sizes, fp32 and bf16."""
     from approx import backend as B
     from approx.layers import MSCA
+    monkeypatch.setenv("CNA_MSCA_FUSED", "1")        # force the one-pass kernel
     torch.manual_seed(C + H)
     m = MSCA(C, 5, (7, 11, 21))
     x = torch.randn(2, C, H, W)
@@ -192,6 +193,22 @@ def test_msca_fused_sd_kernel_vs_oracle(C, H, W, dt):
     n0 = B.launch_count()
     md(x.cuda().to(dt))
     assert B.launch_count() - n0 <= 3       # cached weights: layout + fused sd + mix/gate
+
+
+@pytest.mark.parametrize("C,H,W", [(32, 40, 50), (64, 33, 32), (160, 16, 17), (96, 7, 9)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_msca_tiled_chain_vs_oracle(C, H, W, dt, monkeypatch):
+    """cna_msca_chain_forward (register-tiled 5x5 + strip kernels enqueued by one C call; the default for single-cascade forms)."""
+    from approx import backend as B
+    from approx.layers import MSCA
+    monkeypatch.setenv("CNA_MSCA_FUSED", "chain")
+    assert B.msca_chain_supported(C, 5, (7, 11, 21), dt)
+    torch.manual_seed(C + H + 1)
+    m = MSCA(C, 5, (7, 11, 21))
+    x = torch.randn(2, C, H, W)
+    ref = _oracle_msca(m, x, dt)
+    y = m.cuda().to(dt)(x.cuda().to(dt))
+    assert O.compare4d(ref.float(), y.float().cpu()) < (TOL if dt == torch.float32 else 3e-3)
 
 
 @pytest.mark.parametrize("decomp,fix", [(1, True), (2, True), (3, False), (0, True)])

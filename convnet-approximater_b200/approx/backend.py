@@ -48,6 +48,7 @@ _SIGS = {
     "cna_svd_small_batched": "ppppiiip",
     "cna_svd_jacobi_large": "piiipppip",
     "cna_l2_recon_loss_grad": "pppppiLfip",
+    "cna_l2_recon_loss_grad_bias": "ppppppiiLfip",
     "cna_conv_taps_wgrad": "ppppiiiiiiiiip",
     "cna_pack_taps_weight_dgrad": "ppiiiip",
     "cna_adamw_step": "ppppLfffffifp",
@@ -547,8 +548,9 @@ def svd_topk(A: torch.Tensor, r: int, max_sweeps: int = 30):
 # ------------------------------------------------------------------------------------------- #
 # reconstruction step
 # ------------------------------------------------------------------------------------------- #
-def l2_recon(y_new, y_old, scale, want_grad=True):
-    """-> (norms (B,) fp32, grad like y_new or None): per-sample ||y_new - y_old||_2 and d(scale*sum_b norm_b)/dy_new."""
+def l2_recon(y_new, y_old, scale, want_grad=True, db=None):
+    """-> (norms (B,) fp32, grad like y_new or None): per-sample ||y_new - y_old||_2 and d(scale*sum_b norm_b)/dy_new.
+    `db` (fp32, (N,)): also filled with the bias gradient sum_p grad[p][n] (N = last dim of the NHWC y)."""
     _ready(y_new)
     assert y_new.shape == y_old.shape and y_new.dtype == y_old.dtype and y_new.is_contiguous() and y_old.is_contiguous()
     Bn = y_new.shape[0]
@@ -557,8 +559,13 @@ def l2_recon(y_new, y_old, scale, want_grad=True):
     norms = torch.empty((Bn,), device=y_new.device, dtype=torch.float32)
     g = torch.empty_like(y_new) if want_grad else None
     with torch.cuda.device(y_new.device):
-        _check(lib().cna_l2_recon_loss_grad(_p(y_new), _p(y_old), _p(scratch), _p(norms), _p(g), Bn, per, float(scale),
-                                            dtype_code(y_new.dtype), _stream(y_new)))
+        if db is not None:
+            assert want_grad and db.dtype == torch.float32 and db.numel() == y_new.shape[-1]
+            _check(lib().cna_l2_recon_loss_grad_bias(_p(y_new), _p(y_old), _p(scratch), _p(norms), _p(g), _p(db), y_new.shape[-1], Bn,
+                                                     per, float(scale), dtype_code(y_new.dtype), _stream(y_new)))
+        else:
+            _check(lib().cna_l2_recon_loss_grad(_p(y_new), _p(y_old), _p(scratch), _p(norms), _p(g), Bn, per, float(scale),
+                                                dtype_code(y_new.dtype), _stream(y_new)))
     return norms, g
 
 

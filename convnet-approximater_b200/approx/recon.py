@@ -86,9 +86,8 @@ class Scheme2Reconstructor:
                                                          torch.zeros(64, K, 1, 3, device=x.device))[0])
                 bias = _ops.bias_f32(L.h_conv)
             y, t = B.lowrank2_fused_with_t(x, wv, wh, bias)
-            norms, g = B.l2_recon(y, y_old.contiguous(), self.l2_weight / gb)
+            norms, g = B.l2_recon(y, y_old.contiguous(), self.l2_weight / gb, db=db)     # loss, dL/dy and dL/db in two passes
             B.wgrad3_tc(g, t, dh, N, K, 1, 0)                               # dL/dWh[n][k][t]
-            B.bias_grad(g, db)
             # dL/dT = g convolved along W with h_conv's flipped, transposed taps (wd: a (K, N, 3, 1) "v_conv" weight)
             gt = B.tapconv3_tc(g, wd, 1)
             B.wgrad3_tc(x, gt, dv, C, K, 0, 1)                              # dL/dWv[k][c][t]

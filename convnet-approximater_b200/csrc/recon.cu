@@ -53,6 +53,81 @@ __global__ void __launch_bounds__(256) l2_grad_kernel(const T* __restrict__ yn, 
         g[off + i] = from_f32<T>((to_f32(ldg(yn + off + i)) - to_f32(ldg(yo + off + i))) * f);
 }
 
+// ---- bf16, 16-byte vectorised variants (per_sample % 8 == 0): the reconstruction step's loss kernels move 3 passes over y, so
+// they are plain HBM streams and want 128-bit accesses; the gradient kernel also accumulates the BIAS gradient
+// (db[n] = sum_p g[p][n]) when the grid stride is a multiple of N, so no separate pass over g is needed. ----
+__device__ __forceinline__ void bf16x8_to_f32(const uint4& v, float (&f)[8]) {
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(u[i] << 16); f[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u); }
+}
+
+__global__ void __launch_bounds__(256) l2_sumsq_v8_kernel(const uint4* __restrict__ yn, const uint4* __restrict__ yo,
+                                                         float* __restrict__ sumsq, long long per_sample8) {
+    const int b = blockIdx.y;
+    const uint4* a = yn + (size_t)b * per_sample8;
+    const uint4* c = yo + (size_t)b * per_sample8;
+    float s = 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_sample8; i += (long long)gridDim.x * blockDim.x) {
+        float fa[8], fc[8];
+        bf16x8_to_f32(__ldg(a + i), fa);
+        bf16x8_to_f32(__ldg(c + i), fc);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const float d = fa[k] - fc[k]; s = fmaf(d, d, s); }
+    }
+    __shared__ float red[8];
+    s = warp_sum_f(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        s = red[threadIdx.x];
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffu, s, o);
+        if (threadIdx.x == 0) atomicAdd(sumsq + b, s);
+    }
+}
+
+// N8 = N / 8 (vectors per pixel); dbias != NULL requires (gridDim.x * 256) % N8 == 0 so a thread always sees the same 8 channels
+__global__ void __launch_bounds__(256) l2_grad_v8_kernel(const uint4* __restrict__ yn, const uint4* __restrict__ yo,
+                                                        const float* __restrict__ sumsq, float* __restrict__ norms,
+                                                        uint4* __restrict__ g, long long per_sample8, float scale,
+                                                        float* __restrict__ dbias, int N8) {
+    extern __shared__ float sdb[];                 // [N] when dbias
+    const int b = blockIdx.y;
+    const float nrm = sqrtf(sumsq[b]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) norms[b] = nrm;
+    const float f = nrm > 0.f ? scale / nrm : 0.f;
+    const size_t off = (size_t)b * per_sample8;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    if (dbias) {
+        for (int i = threadIdx.x; i < N8 * 8; i += 256) sdb[i] = 0.f;
+        __syncthreads();
+    }
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_sample8; i += (long long)gridDim.x * blockDim.x) {
+        float fa[8], fc[8];
+        bf16x8_to_f32(__ldg(yn + off + i), fa);
+        bf16x8_to_f32(__ldg(yo + off + i), fc);
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            __nv_bfloat162 t = __floats2bfloat162_rn((fa[2 * k] - fc[2 * k]) * f, (fa[2 * k + 1] - fc[2 * k + 1]) * f);
+            o[k] = *reinterpret_cast<uint32_t*>(&t);
+            acc[2 * k] += __uint_as_float(o[k] << 16);            // the bias gradient sums the ROUNDED g, like a pass over g would
+            acc[2 * k + 1] += __uint_as_float(o[k] & 0xffff0000u);
+        }
+        g[off + i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    if (dbias) {
+        const int ch = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) % N8) * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) atomicAdd(sdb + ch + k, acc[k]);
+        __syncthreads();
+        for (int i = threadIdx.x; i < N8 * 8; i += 256) atomicAdd(dbias + i, sdb[i]);
+    }
+}
+
 // Weight gradient of a stride-1 tap convolution:  dw[o][i][t] += sum_p x[p shifted by tap t][i] * g[p][o]
 // One CTA: a 32(i) x 64(o) block of one tap, over a slab of output pixels; fp32 atomics into dw.
 constexpr int WG_I = 32, WG_O = 64, WG_P = 32;
@@ -171,12 +246,37 @@ using namespace cna;
 
 extern "C" {
 
-int cna_l2_recon_loss_grad(const void* y_new, const void* y_old, float* sumsq_scratch, float* norms, void* grad,
-                           int B, long long per_sample, float scale, int dtype, void* stream) {
+static int l2_recon_impl(const void* y_new, const void* y_old, float* sumsq_scratch, float* norms, void* grad, float* dbias, int N,
+                         int B, long long per_sample, float scale, int dtype, void* stream) {
     CNA_CHECK(y_new && y_old && sumsq_scratch && norms, "null pointer");
     CNA_CHECK(B > 0 && B <= 65535 && per_sample > 0, "bad dims");
+    CNA_CHECK(dbias == nullptr || (grad != nullptr && N > 0 && per_sample % N == 0), "bias gradient needs the gradient tensor and N");
     cudaStream_t st = as_stream(stream);
     CNA_CUDA(cudaMemsetAsync(sumsq_scratch, 0, sizeof(float) * B, st));
+    const bool aligned = ((reinterpret_cast<uintptr_t>(y_new) | reinterpret_cast<uintptr_t>(y_old) | reinterpret_cast<uintptr_t>(grad)) & 15) == 0;
+    if (dtype == CNA_BF16 && per_sample % 8 == 0 && aligned) {
+        const long long ps8 = per_sample / 8;
+        // ~8 CTAs per SM in total: enough to stream at full rate, few enough that the per-CTA bias atomics stay cheap
+        int slabs = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(ceil_div_ll(ps8, 256), 64), ceil_div_ll(148 * 8, B)));
+        const int N8 = N / 8;
+        // bias-gradient fusion: every thread must keep the same 8 channels across its grid-stride iterations
+        bool fuse_db = dbias != nullptr && N % 8 == 0 && N8 <= 2048;
+        if (fuse_db) {
+            while (slabs > 1 && ((long long)slabs * 256) % N8 != 0) --slabs;
+            fuse_db = ((long long)slabs * 256) % N8 == 0;
+        }
+        dim3 grid(slabs, B);
+        l2_sumsq_v8_kernel<<<grid, 256, 0, st>>>((const uint4*)y_new, (const uint4*)y_old, sumsq_scratch, ps8);
+        CNA_LAUNCH_OK();
+        if (grad) {
+            if (fuse_db) CNA_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * N, st));
+            l2_grad_v8_kernel<<<grid, 256, fuse_db ? sizeof(float) * N : 0, st>>>((const uint4*)y_new, (const uint4*)y_old, sumsq_scratch, norms,
+                                                                                (uint4*)grad, ps8, scale, fuse_db ? dbias : nullptr, N8);
+            CNA_LAUNCH_OK();
+            if (dbias && !fuse_db) return cna_bias_grad(grad, dbias, (long long)B * (per_sample / N), N, dtype, stream);
+        }
+        return 0;
+    }
     int slabs = (int)std::min<long long>(ceil_div_ll(per_sample, 256 * 8), 64);
     dim3 grid(slabs, B);
     if (dtype == CNA_F32) l2_sumsq_kernel<float><<<grid, 256, 0, st>>>((const float*)y_new, (const float*)y_old, sumsq_scratch, per_sample);
@@ -187,8 +287,20 @@ int cna_l2_recon_loss_grad(const void* y_new, const void* y_old, float* sumsq_sc
         if (dtype == CNA_F32) l2_grad_kernel<float><<<grid, 256, 0, st>>>((const float*)y_new, (const float*)y_old, sumsq_scratch, norms, (float*)grad, per_sample, scale);
         else l2_grad_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)y_new, (const __nv_bfloat16*)y_old, sumsq_scratch, norms, (__nv_bfloat16*)grad, per_sample, scale);
         CNA_LAUNCH_OK();
+        if (dbias) return cna_bias_grad(grad, dbias, (long long)B * (per_sample / N), N, dtype, stream);
     }
     return 0;
+}
+
+int cna_l2_recon_loss_grad(const void* y_new, const void* y_old, float* sumsq_scratch, float* norms, void* grad,
+                           int B, long long per_sample, float scale, int dtype, void* stream) {
+    return l2_recon_impl(y_new, y_old, sumsq_scratch, norms, grad, nullptr, 0, B, per_sample, scale, dtype, stream);
+}
+
+int cna_l2_recon_loss_grad_bias(const void* y_new, const void* y_old, float* sumsq_scratch, float* norms, void* grad, float* dbias,
+                                int N, int B, long long per_sample, float scale, int dtype, void* stream) {
+    CNA_CHECK(dbias != nullptr, "null pointer");
+    return l2_recon_impl(y_new, y_old, sumsq_scratch, norms, grad, dbias, N, B, per_sample, scale, dtype, stream);
 }
 
 int cna_conv_taps_wgrad(const void* x, const void* g, float* dw, float* dbias, int B, int H, int W, int C, int N,

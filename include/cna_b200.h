@@ -180,6 +180,10 @@ int cna_msca_equiv_kernel(const float* w1cat, const float* b1, const float* w2ca
  * src/approx/hooks/finetune.py:80-82,315-322 (scale = l2_weight / (L * B_global)). */
 int cna_l2_recon_loss_grad(const void* y_new, const void* y_old, float* sumsq_scratch, float* norms, void* grad,
                            int B, long long per_sample, float scale, int dtype, void* stream);
+/* Same, additionally producing the bias gradient dbias[n] = sum_p grad[p][n] (fp32, overwritten; N = channels of y) — fused into
+ * the gradient kernel for bf16 tensors so the step needs no separate pass over dL/dy. */
+int cna_l2_recon_loss_grad_bias(const void* y_new, const void* y_old, float* sumsq_scratch, float* norms, void* grad, float* dbias,
+                                int N, int B, long long per_sample, float scale, int dtype, void* stream);
 /* Weight (and bias) gradient of a stride-1 'same' tap convolution (see cna_conv_taps_forward):
  *   dw[o][i][t] = sum_p x[p shifted by tap t][i] * g[p][o]   (reference OIHW layout, fp32; overwritten)
  *   dbias[o]    = sum_p g[p][o]                               (NULL to skip)

@@ -231,3 +231,31 @@ def test_graph_replay_matches_eager_steps():
     rel = (graphed.master - eager.master).norm() / eager.master.norm()
     assert rel < 2e-3, rel               # same kernels; eager packs from the bf16 parameters, the graph from the fp32 master
     assert torch.isfinite(loss)
+
+
+@pytest.mark.parametrize("case", [(4, 64, 28, 28, 32, 128), (2, 128, 14, 30, 64, 256)])
+def test_tensor_core_gradients_match_autograd_bf16(case):
+    """Scheme2Reconstructor.gradients on the tcgen05 path (forward + T, fused loss/bias gradient, MN-major weight gradients,
+    3-tap data gradient) against torch autograd through the same bf16 layer."""
+    from approx.layers import LowRankExpConvV2
+    from approx.recon import Scheme2Reconstructor
+    from approx import backend as B
+    Bn, C, H, W, K, N = case
+    torch.manual_seed(31)
+    layer = LowRankExpConvV2(C, K, (3, 3), (1, 1), (1, 1), out_channels=N).cuda().bfloat16()
+    x = torch.randn(Bn, C, H, W, device="cuda").bfloat16()
+    y_old = torch.randn(Bn, N, H, W, device="cuda").bfloat16()
+    # autograd reference with stock convs on the same parameters (bf16 forward like the reference's modules)
+    v = layer.v_conv.weight.detach().clone().requires_grad_(True)
+    h = layer.h_conv.weight.detach().clone().requires_grad_(True)
+    b = layer.h_conv.bias.detach().clone().requires_grad_(True)
+    y = F.conv2d(F.conv2d(x, v, None, 1, (1, 0)), h, b, 1, (0, 1))
+    loss = (y.float() - y_old.float()).flatten(1).norm(dim=1).mean()
+    loss.backward()
+    rec = Scheme2Reconstructor(layer)
+    norms = rec.gradients(B.to_nhwc(x, B.round_up(C, 16)).contiguous(), B.to_nhwc(y_old).contiguous())
+    dv, dh, db = rec._views(rec.grad)
+    assert abs(norms.mean().item() - loss.item()) / loss.item() < 5e-3
+    for got, ref in ((dv, v.grad), (dh, h.grad), (db, b.grad)):
+        ref = ref.float().reshape(got.shape)
+        assert (got - ref).norm() / ref.norm() < 3e-2, ((got - ref).norm() / ref.norm()).item()

@@ -39,6 +39,9 @@ _SIGS = {
     "cna_tapconv3_tc_forward": "pppiiiiiip",
     "cna_wgrad3_tc": "pppiiiiiiiiip",
     "cna_bias_grad": "ppLiip",
+    "cna_dwconv_wgrad": "pppiiiiiiiiip",
+    "cna_fix_padding_bias_grad": "ppiiiiiip",
+    "cna_mul": "pppLip",
     "cna_lowrank2_fused_forward_traced": "pppppiiiiiiiippi",
     "cna_maxpool2x2": "ppiiiiip",
     "cna_msca_sd_supported": "iiipi",
@@ -448,6 +451,38 @@ def lowrank2_pack_into(v_w, h_w, wv, wh):
     with torch.cuda.device(v_w.device):
         _check(lib().cna_lowrank2_pack(_p(v_w), _p(h_w), _p(wv), _p(wh), C, K, N, d, wv.shape[2], wv.shape[1], _stream(v_w)))
     return wv, wh
+
+
+def dwconv_wgrad(x, g, kh, kw):
+    """Depthwise (multiplier 1, stride 1, 'same') weight gradient: x, g (B,H,W,C) NHWC -> dw fp32 (C,1,kh,kw)."""
+    _ready(x)
+    Bn, H, W, C = x.shape
+    assert g.shape == x.shape and g.dtype == x.dtype and x.is_contiguous() and g.is_contiguous()
+    dw = torch.empty((C, 1, kh, kw), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _check(lib().cna_dwconv_wgrad(_p(x), _p(g), _p(dw), Bn, H, W, C, kh, kw, kh // 2, kw // 2, dtype_code(x.dtype), _stream(x)))
+    return dw
+
+
+def fix_padding_bias_grad(g, p):
+    """Gradient of FixPaddingBias.res: g (B,H,W,C) NHWC -> fp32 (2,C,p)."""
+    _ready(g)
+    Bn, H, W, C = g.shape
+    assert g.is_contiguous()
+    dres = torch.empty((2, C, p), device=g.device, dtype=torch.float32)
+    with torch.cuda.device(g.device):
+        _check(lib().cna_fix_padding_bias_grad(_p(g), _p(dres), Bn, H, W, C, int(p), dtype_code(g.dtype), _stream(g)))
+    return dres
+
+
+def mul(a, b):
+    """Elementwise product of two same-shape contiguous tensors."""
+    _ready(a)
+    assert a.shape == b.shape and a.dtype == b.dtype and a.is_contiguous() and b.is_contiguous()
+    out = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        _check(lib().cna_mul(_p(a), _p(b), _p(out), a.numel(), dtype_code(a.dtype), _stream(a)))
+    return out
 
 
 def bias_grad(g, db):

@@ -51,6 +51,12 @@ class MSCA(nn.Module):
 
     def forward(self, x):
         _ops.check_input(x)
+        # model.train() + autograd (the reference's L2Reconstruct fine-tuning, hooks/finetune.py:275,329): op-by-op path with
+        # backward kernels; model.eval() or no_grad (every inference hook of the reference): the fused kernels
+        if (self.training and torch.is_grad_enabled()
+                and (x.requires_grad or any(p.requires_grad for p in self.parameters()))):
+            from . import _msca_autograd
+            return _msca_autograd.msca_train_forward(self, x)
         return B.from_nhwc(self.forward_nhwc(B.to_nhwc(x)))
 
     def switchable_layer(self):

@@ -199,6 +199,17 @@ int cna_conv_taps_wgrad(const void* x, const void* g, float* dw, float* dbias, i
  * fp32 / any-shape path. */
 int cna_wgrad3_tc(const void* a, const void* bm, float* dw, int B, int H, int W, int ca_stride, int Ca, int kb_stride, int kb, int axis,
                   int wide_is_input, void* stream);
+/* ---- backward pieces of the depthwise layers (MSCA training; csrc/dw_backward.cu) ---------------------------------------
+ * Replaces autograd through nn.Conv2d(groups=C), FixPaddingBias and the `x *` gate (src/approx/hooks/finetune.py:329-330 with an
+ * MSCA block's sd_convs trainable).  The DATA gradient of a stride-1 'same' depthwise conv is cna_dwconv_forward on the flipped filter.
+ * dw[c][i][j] = sum_{b,h,w} x[b,h+i-pad_h,w+j-pad_w,c] * g[b,h,w,c]  (fp32, (C,1,kh,kw) layout, overwritten). */
+int cna_dwconv_wgrad(const void* x, const void* g, float* dw, int B, int H, int W, int C, int kh, int kw, int pad_h, int pad_w, int dtype,
+                     void* stream);
+/* dres[2][C][p] (fp32, overwritten): gradient of FixPaddingBias' residues = sums of g over (b, w) on the touched border rows. */
+int cna_fix_padding_bias_grad(const void* g, float* dres, int B, int H, int W, int C, int p, int dtype, void* stream);
+/* out = a * b elementwise (the gate and its gradients). */
+int cna_mul(const void* a, const void* b, void* out, long long count, int dtype, void* stream);
+
 /* dbias[n] = sum_p g[p][n] over P pixels (fp32, overwritten): the bias gradient of any conv whose output gradient is g. */
 int cna_bias_grad(const void* g, float* dbias, long long P, int N, int dtype, void* stream);
 /* Packs w[o][i][t] for the INPUT gradient of a tap conv: packed[taps-1-t][o][i]; feed to cna_conv_taps_forward with

@@ -161,7 +161,7 @@ def test_bf16_msca_against_bf16_oracle(golden):
           for i in range(3)]
     ref = O.msca_forward(x, sd["conv0.weight"], sd["conv0.bias"], lambda a: O.parallel_forward(a, br, True),
                          sd["channel_mix.weight"], sd["channel_mix.bias"])
-    y = mb.cuda()(x.cuda())
+    y = mb.cuda().eval()(x.cuda())
     assert O.compare4d(ref.float(), y.float().cpu()) < 3e-3
 
 
@@ -185,7 +185,7 @@ def test_msca_fused_sd_kernel_vs_oracle(C, H, W, dt, monkeypatch):
     m = MSCA(C, 5, (7, 11, 21))
     x = torch.randn(2, C, H, W)
     ref = _oracle_msca(m, x, dt)
-    md = m.cuda().to(dt)
+    md = m.cuda().to(dt).eval()          # inference, as the reference's hooks run it (model.eval()); train() mode takes the autograd path
     n0 = B.launch_count()
     y = md(x.cuda().to(dt))
     assert B.launch_count() - n0 <= 12      # packing + layout + 2 compute kernels (fused sd, mix+gate)
@@ -207,7 +207,7 @@ def test_msca_tiled_chain_vs_oracle(C, H, W, dt, monkeypatch):
     m = MSCA(C, 5, (7, 11, 21))
     x = torch.randn(2, C, H, W)
     ref = _oracle_msca(m, x, dt)
-    y = m.cuda().to(dt)(x.cuda().to(dt))
+    y = m.cuda().to(dt).eval()(x.cuda().to(dt))
     assert O.compare4d(ref.float(), y.float().cpu()) < (TOL if dt == torch.float32 else 3e-3)
 
 
@@ -239,5 +239,66 @@ def test_msca_rep_fused_matches_unfused(decomp, fix):
             yy = O.parallel_forward(a, brs, False)
             return O.fix_padding_bias(yy, r, 10) if fix else yy
     ref = O.msca_forward(x, sd["conv0.weight"], sd["conv0.bias"], sdf, sd["channel_mix.weight"], sd["channel_mix.bias"])
-    y = tgt.cuda()(x.cuda())
+    y = tgt.cuda().eval()(x.cuda())
     assert O.compare4d(ref, y.cpu()) < 5e-5
+
+
+def _torch_msca_forward(m, x):
+    """Stock-torch restatement of MSCA.forward for any sd_convs form (the reference's modules, layers/msca.py:25-26,
+    depth_seperable_conv.py:12-16,45-47,57-61) — the autograd reference for the training path."""
+    import torch.nn.functional as F
+    from approx.layers.depth_seperable_conv import CascadeConv, FixPaddingBias, ParallelConv
+    C = m.num_channel
+    conv = lambda c, t: F.conv2d(t, c.weight, c.bias, 1, c.padding, 1, C)
+    a = conv(m.conv0, x)
+    sd, fix = m.sd_convs, None
+    if isinstance(sd, nn.Sequential):
+        sd, fix = sd[0], sd[1]
+    if isinstance(sd, ParallelConv):
+        s = sum([conv(br.conv2, conv(br.conv1, a)) for br in sd.cascades()] + ([a] if sd.has_identity else []))
+    elif isinstance(sd, CascadeConv):
+        s = conv(sd.conv2, conv(sd.conv1, a))
+    else:
+        s = conv(sd, a)
+    if fix is not None:
+        p2 = min(s.shape[2], fix.p)
+        top = torch.zeros_like(s); bot = torch.zeros_like(s)
+        top[:, :, :p2, :] = fix.res[0][None, :, :p2, None]
+        bot[:, :, -p2:, :] = fix.res[1][None, :, -p2:, None]
+        s = s + top + bot
+    return x * F.conv2d(s, m.channel_mix.weight, m.channel_mix.bias)
+
+
+@pytest.mark.parametrize("form", ["original", "d1_fix", "d0_fix", "d3"])
+def test_msca_training_path_gradients_vs_autograd(form):
+    """model.train(): forward and every parameter / input gradient of the op-by-op CUDA path against torch autograd (fp32)."""
+    import copy
+    from approx.core import MscaRep
+    from approx.layers import MSCA
+    torch.manual_seed(13)
+    C, H, W = 32, 14, 19
+    m = MSCA(C, 5, (7, 11, 21))
+    if form != "original":
+        d, f = {"d1_fix": (1, True), "d0_fix": (0, True), "d3": (3, False)}[form]
+        app = MscaRep(decomp=d, fix=f)
+        sub = app.initialize(m)
+        with contextlib.redirect_stdout(io.StringIO()):
+            app.optimize(sub)
+        m = app.postprocess(sub)
+    ref = copy.deepcopy(m)                              # torch reference stays on the CPU: exact fp32 (cuDNN would use TF32)
+    m = m.cuda().train()
+    x = torch.randn(2, C, H, W)
+    gy = torch.randn(2, C, H, W)
+    x1 = x.clone().cuda().requires_grad_(True)
+    y1 = m(x1)
+    y1.backward(gy.cuda())
+    x2 = x.clone().requires_grad_(True)
+    y2 = _torch_msca_forward(ref, x2)
+    y2.backward(gy)
+    assert O.compare4d(y2.detach(), y1.detach().cpu()) < 1e-5
+    assert (x1.grad.cpu() - x2.grad).norm() / x2.grad.norm() < 1e-4
+    for (n1, p1), (n2, p2) in zip(m.named_parameters(), ref.named_parameters()):
+        assert n1 == n2
+        assert p1.grad is not None, n1
+        denom = p2.grad.norm().clamp_min(1e-6)
+        assert (p1.grad.cpu() - p2.grad).norm() / denom < 2e-4, (n1, ((p1.grad.cpu() - p2.grad).norm() / denom).item())

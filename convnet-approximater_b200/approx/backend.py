@@ -39,7 +39,8 @@ _SIGS = {
     "cna_tapconv3_tc_forward": "pppiiiiiip",
     "cna_wgrad3_tc": "pppiiiiiiiiip",
     "cna_bias_grad": "ppLiip",
-    "cna_dwconv_wgrad": "pppiiiiiiiiip",
+    "cna_dwconv_wgrad": "pppiiiiiiiiiip",
+    "cna_dwconv_dgrad": "pppiiiiiiiiiip",
     "cna_fix_padding_bias_grad": "ppiiiiiip",
     "cna_mul": "pppLip",
     "cna_lowrank2_fused_forward_traced": "pppppiiiiiiiippi",
@@ -454,14 +455,28 @@ def lowrank2_pack_into(v_w, h_w, wv, wh):
 
 
 def dwconv_wgrad(x, g, kh, kw):
-    """Depthwise (multiplier 1, stride 1, 'same') weight gradient: x, g (B,H,W,C) NHWC -> dw fp32 (C,1,kh,kw)."""
+    """Depthwise (stride 1, 'same', any channel multiplier) weight gradient: x (B,H,W,Cin), g (B,H,W,Cin*mult) -> dw fp32 (Cout,1,kh,kw)."""
     _ready(x)
-    Bn, H, W, C = x.shape
-    assert g.shape == x.shape and g.dtype == x.dtype and x.is_contiguous() and g.is_contiguous()
-    dw = torch.empty((C, 1, kh, kw), device=x.device, dtype=torch.float32)
+    Bn, H, W, Cin = x.shape
+    Cout = g.shape[3]
+    assert g.shape[:3] == x.shape[:3] and Cout % Cin == 0 and g.dtype == x.dtype and x.is_contiguous() and g.is_contiguous()
+    dw = torch.empty((Cout, 1, kh, kw), device=x.device, dtype=torch.float32)
     with torch.cuda.device(x.device):
-        _check(lib().cna_dwconv_wgrad(_p(x), _p(g), _p(dw), Bn, H, W, C, kh, kw, kh // 2, kw // 2, dtype_code(x.dtype), _stream(x)))
+        _check(lib().cna_dwconv_wgrad(_p(x), _p(g), _p(dw), Bn, H, W, Cin, Cout // Cin, kh, kw, kh // 2, kw // 2, dtype_code(x.dtype),
+                                      _stream(x)))
     return dw
+
+
+def dwconv_dgrad(g, wpk, mult, kh, kw):
+    """Data gradient of a stride-1 'same' depthwise conv with channel multiplier: g (B,H,W,Cin*mult), wpk [kh*kw][Cin*mult] -> (B,H,W,Cin)."""
+    _ready(g)
+    Bn, H, W, Cout = g.shape
+    assert Cout % mult == 0 and wpk.shape == (kh * kw, Cout) and wpk.dtype == g.dtype and g.is_contiguous()
+    gx = torch.empty((Bn, H, W, Cout // mult), device=g.device, dtype=g.dtype)
+    with torch.cuda.device(g.device):
+        _check(lib().cna_dwconv_dgrad(_p(g), _p(wpk), _p(gx), Bn, H, W, Cout // mult, int(mult), kh, kw, kh // 2, kw // 2,
+                                      dtype_code(g.dtype), _stream(g)))
+    return gx
 
 
 def fix_padding_bias_grad(g, p):

@@ -20,7 +20,7 @@ def _f32_grad_like(param, g32):
 
 
 class _DwConv(torch.autograd.Function):
-    """Depthwise conv (groups = C, multiplier 1, stride 1, 'same' padding) on an NHWC tensor."""
+    """Depthwise conv (groups = Cin, any channel multiplier, stride 1, 'same' padding) on an NHWC tensor."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, conv):
@@ -35,10 +35,15 @@ class _DwConv(torch.autograd.Function):
         g = g.contiguous()
         kh, kw = conv.kernel_size
         gx = gw = gb = None
+        mult = conv.out_channels // conv.in_channels
         if ctx.needs_input_grad[0]:
-            wflip = _ops.cached(conv, "dw_w_flipped", (conv.weight,), g.dtype,
-                                lambda: B.pack_dw(conv.weight.detach().flip(2, 3).contiguous(), g.dtype))
-            gx = B.dwconv(g, wflip, None, 1, kh, kw, (1, 1), (kh // 2, kw // 2))
+            if mult == 1:      # the forward (register-tiled) kernels on the flipped filter
+                wflip = _ops.cached(conv, "dw_w_flipped", (conv.weight,), g.dtype,
+                                    lambda: B.pack_dw(conv.weight.detach().flip(2, 3).contiguous(), g.dtype))
+                gx = B.dwconv(g, wflip, None, 1, kh, kw, (1, 1), (kh // 2, kw // 2))
+            else:
+                wpk = _ops.cached(conv, "dw_w", (conv.weight,), g.dtype, lambda: B.pack_dw(conv.weight, g.dtype))
+                gx = B.dwconv_dgrad(g, wpk, mult, kh, kw)
         if ctx.needs_input_grad[1]:
             gw = _f32_grad_like(conv.weight, B.dwconv_wgrad(x, g, kh, kw))
         if conv.bias is not None and ctx.needs_input_grad[2]:
@@ -114,11 +119,12 @@ class _Add(torch.autograd.Function):
 
 
 def _dw(conv, x):
-    ok = (conv.groups == conv.in_channels == conv.out_channels and tuple(conv.stride) == (1, 1) and conv.dilation == (1, 1)
+    ok = (conv.groups == conv.in_channels and conv.out_channels % conv.in_channels == 0 and tuple(conv.stride) == (1, 1)
+          and conv.dilation == (1, 1)
           and tuple(conv.padding) == (conv.kernel_size[0] // 2, conv.kernel_size[1] // 2)
           and conv.kernel_size[0] % 2 == 1 and conv.kernel_size[1] % 2 == 1)
     if not ok:
-        raise NotImplementedError("training kernels cover stride-1 'same' depthwise convolutions with channel multiplier 1")
+        raise NotImplementedError("training kernels cover stride-1 'same' depthwise convolutions")
     return _DwConv.apply(x, conv.weight, conv.bias, conv)
 
 
@@ -154,3 +160,16 @@ def msca_train_forward(msca, x):
     s = sd_convs_train(msca.sd_convs, a0)
     m = _Conv1x1.apply(s, msca.channel_mix.weight, msca.channel_mix.bias, msca.channel_mix)
     return _Mul.apply(m, xn).permute(0, 3, 1, 2)
+
+
+def lowrank1_train_forward(layer, x):
+    """LowRankExpConvV1 (scheme 1) with a full autograd graph: s_conv (grouped d x d conv with channel multiplier, or its
+    separable d x 1 . 1 x d form after decomp()) then the 1x1 d_conv (reference layers/low_rank_conv.py:51-52)."""
+    from .low_rank_conv import SeparableConv
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    if isinstance(layer.s_conv, SeparableConv):
+        t = _dw(layer.s_conv.h_conv, _dw(layer.s_conv.v_conv, xn))
+    else:
+        t = _dw(layer.s_conv, xn)
+    y = _Conv1x1.apply(t, layer.d_conv.weight, layer.d_conv.bias, layer.d_conv)
+    return y.permute(0, 3, 1, 2)

@@ -69,6 +69,13 @@ class LowRankExpConvV1(nn.Module):
 
     def forward(self, x):
         _ops.check_input(x)
+        # model.train() + autograd (the reference's L2Reconstruct fine-tuning of the AlexNet layers): op-by-op path with backward
+        # kernels; model.eval() / no_grad: the inference kernels
+        if (self.training and torch.is_grad_enabled() and self.stride == (1, 1)
+                and self.padding == (self.kernel_size[0] // 2, self.kernel_size[1] // 2)
+                and (x.requires_grad or any(p.requires_grad for p in self.parameters()))):
+            from . import _msca_autograd
+            return _msca_autograd.lowrank1_train_forward(self, x)
         return B.from_nhwc(self.forward_nhwc(B.to_nhwc(x)))
 
     def decomp(self):

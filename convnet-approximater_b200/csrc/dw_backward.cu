@@ -15,8 +15,9 @@ constexpr int DWG_LANES = 8;    // pixel lanes per channel
 // grid (ceil(C/32), slabs, taps): one tap, 32 channels, a slab of pixels; fp32 atomics into dw[c][tap]
 template <typename T>
 __global__ void __launch_bounds__(DWG_CH * DWG_LANES)
-dw_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ g, float* __restrict__ dw, int B, int H, int W, int C, int kh, int kw,
-                int ph, int pw, long long pix_per_cta) {
+dw_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ g, float* __restrict__ dw, int B, int H, int W, int C, int mult, int kh,
+                int kw, int ph, int pw, long long pix_per_cta) {   // C = OUTPUT channels (= Cin * mult); output channel c reads input channel c / mult
+    const int Cin = C / mult;
     const int c = blockIdx.x * DWG_CH + (threadIdx.x & (DWG_CH - 1));
     const int lane = threadIdx.x / DWG_CH;
     const int tap = blockIdx.z, ti = tap / kw, tj = tap - ti * kw;
@@ -30,7 +31,7 @@ dw_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ g, float* __restr
             const int hi = h + ti - ph, wi = w + tj - pw;
             if (hi < 0 || hi >= H || wi < 0 || wi >= W) continue;
             const long long q = p + (long long)(ti - ph) * W + (tj - pw);
-            acc = fmaf(to_f32(ldg(x + q * C + c)), to_f32(ldg(g + p * C + c)), acc);
+            acc = fmaf(to_f32(ldg(x + q * Cin + c / mult)), to_f32(ldg(g + p * C + c)), acc);
         }
     }
     __shared__ float red[DWG_LANES][DWG_CH + 1];
@@ -72,6 +73,35 @@ fix_bias_grad_kernel(const T* __restrict__ g, float* __restrict__ dres, int B, i
     }
 }
 
+// Data gradient of a stride-1 'same' depthwise conv with channel multiplier `mult`:
+//   gx[b,h,w,ci] = sum_m sum_{i,j} g[b, h-(i-ph), w-(j-pw), ci*mult+m] * w[ci*mult+m][i][j]        (w packed [kh*kw][Cout])
+template <typename T>
+__global__ void __launch_bounds__(256)
+dw_dgrad_mult_kernel(const T* __restrict__ g, const T* __restrict__ w, T* __restrict__ gx, int B, int H, int W, int Cin, int mult, int kh,
+                     int kw, int ph, int pw) {
+    const int Cout = Cin * mult;
+    const long long total = (long long)B * H * W * Cin;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(idx % Cin);
+        const long long pix = idx / Cin;
+        const int wq = (int)(pix % W), hq = (int)((pix / W) % H);
+        const int b = (int)(pix / ((long long)W * H));
+        float acc = 0.f;
+        for (int i = 0; i < kh; ++i) {
+            const int ho = hq - (i - ph);
+            if (ho < 0 || ho >= H) continue;
+            for (int j = 0; j < kw; ++j) {
+                const int wo = wq - (j - pw);
+                if (wo < 0 || wo >= W) continue;
+                const T* gp = g + (((size_t)b * H + ho) * W + wo) * Cout + (size_t)ci * mult;
+                const T* wp = w + (size_t)(i * kw + j) * Cout + (size_t)ci * mult;
+                for (int m = 0; m < mult; ++m) acc = fmaf(to_f32(ldg(gp + m)), to_f32(ldg(wp + m)), acc);
+            }
+        }
+        gx[idx] = from_f32<T>(acc);
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) mul_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, long long n) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -84,10 +114,11 @@ using namespace cna;
 
 extern "C" {
 
-int cna_dwconv_wgrad(const void* x, const void* g, float* dw, int B, int H, int W, int C, int kh, int kw, int pad_h, int pad_w, int dtype,
-                     void* stream) {
-    CNA_CHECK(x && g && dw && B > 0 && H > 0 && W > 0 && C > 0 && kh > 0 && kw > 0, "bad arguments");
-    CNA_CHECK(2 * pad_h == kh - 1 && 2 * pad_w == kw - 1, "implemented for stride-1 'same' depthwise convolutions (multiplier 1)");
+int cna_dwconv_wgrad(const void* x, const void* g, float* dw, int B, int H, int W, int Cin, int mult, int kh, int kw, int pad_h, int pad_w,
+                     int dtype, void* stream) {
+    CNA_CHECK(x && g && dw && B > 0 && H > 0 && W > 0 && Cin > 0 && mult > 0 && kh > 0 && kw > 0, "bad arguments");
+    const int C = Cin * mult;
+    CNA_CHECK(2 * pad_h == kh - 1 && 2 * pad_w == kw - 1, "implemented for stride-1 'same' depthwise convolutions");
     cudaStream_t st = as_stream(stream);
     const int taps = kh * kw;
     CNA_CHECK(taps <= 65535, "too many taps");
@@ -98,8 +129,22 @@ int cna_dwconv_wgrad(const void* x, const void* g, float* dw, int B, int H, int 
     const long long ppc = ceil_div_ll(P, slabs);
     slabs = (int)ceil_div_ll(P, ppc);
     dim3 grid(cblocks, slabs, taps);
-    if (dtype == CNA_F32) dw_wgrad_kernel<float><<<grid, DWG_CH * DWG_LANES, 0, st>>>((const float*)x, (const float*)g, dw, B, H, W, C, kh, kw, pad_h, pad_w, ppc);
-    else if (dtype == CNA_BF16) dw_wgrad_kernel<__nv_bfloat16><<<grid, DWG_CH * DWG_LANES, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)g, dw, B, H, W, C, kh, kw, pad_h, pad_w, ppc);
+    if (dtype == CNA_F32) dw_wgrad_kernel<float><<<grid, DWG_CH * DWG_LANES, 0, st>>>((const float*)x, (const float*)g, dw, B, H, W, C, mult, kh, kw, pad_h, pad_w, ppc);
+    else if (dtype == CNA_BF16) dw_wgrad_kernel<__nv_bfloat16><<<grid, DWG_CH * DWG_LANES, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)g, dw, B, H, W, C, mult, kh, kw, pad_h, pad_w, ppc);
+    else CNA_FAIL("unsupported dtype");
+    CNA_LAUNCH_OK();
+    return 0;
+}
+
+int cna_dwconv_dgrad(const void* g, const void* w_packed, void* gx, int B, int H, int W, int Cin, int mult, int kh, int kw, int pad_h,
+                     int pad_w, int dtype, void* stream) {
+    CNA_CHECK(g && w_packed && gx && B > 0 && H > 0 && W > 0 && Cin > 0 && mult > 0 && kh > 0 && kw > 0, "bad arguments");
+    CNA_CHECK(2 * pad_h == kh - 1 && 2 * pad_w == kw - 1, "implemented for stride-1 'same' depthwise convolutions");
+    const long long total = (long long)B * H * W * Cin;
+    const int grid = (int)std::min<long long>(ceil_div_ll(total, 256), 148LL * 64);
+    cudaStream_t st = as_stream(stream);
+    if (dtype == CNA_F32) dw_dgrad_mult_kernel<float><<<grid, 256, 0, st>>>((const float*)g, (const float*)w_packed, (float*)gx, B, H, W, Cin, mult, kh, kw, pad_h, pad_w);
+    else if (dtype == CNA_BF16) dw_dgrad_mult_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)w_packed, (__nv_bfloat16*)gx, B, H, W, Cin, mult, kh, kw, pad_h, pad_w);
     else CNA_FAIL("unsupported dtype");
     CNA_LAUNCH_OK();
     return 0;

@@ -202,9 +202,13 @@ int cna_wgrad3_tc(const void* a, const void* bm, float* dw, int B, int H, int W,
 /* ---- backward pieces of the depthwise layers (MSCA training; csrc/dw_backward.cu) ---------------------------------------
  * Replaces autograd through nn.Conv2d(groups=C), FixPaddingBias and the `x *` gate (src/approx/hooks/finetune.py:329-330 with an
  * MSCA block's sd_convs trainable).  The DATA gradient of a stride-1 'same' depthwise conv is cna_dwconv_forward on the flipped filter.
- * dw[c][i][j] = sum_{b,h,w} x[b,h+i-pad_h,w+j-pad_w,c] * g[b,h,w,c]  (fp32, (C,1,kh,kw) layout, overwritten). */
-int cna_dwconv_wgrad(const void* x, const void* g, float* dw, int B, int H, int W, int C, int kh, int kw, int pad_h, int pad_w, int dtype,
-                     void* stream);
+ * dw[co][i][j] = sum_{b,h,w} x[b,h+i-pad_h,w+j-pad_w,co/mult] * g[b,h,w,co]  (fp32, (Cin*mult,1,kh,kw) layout, overwritten). */
+int cna_dwconv_wgrad(const void* x, const void* g, float* dw, int B, int H, int W, int Cin, int mult, int kh, int kw, int pad_h, int pad_w,
+                     int dtype, void* stream);
+/* Data gradient for any channel multiplier (scheme 1's s_conv): gx[.,ci] = sum_m sum_taps g[shifted, ci*mult+m] * w[ci*mult+m][tap];
+ * w_packed [kh*kw][Cin*mult] as for cna_dwconv_forward (NOT flipped). */
+int cna_dwconv_dgrad(const void* g, const void* w_packed, void* gx, int B, int H, int W, int Cin, int mult, int kh, int kw, int pad_h,
+                     int pad_w, int dtype, void* stream);
 /* dres[2][C][p] (fp32, overwritten): gradient of FixPaddingBias' residues = sums of g over (b, w) on the touched border rows. */
 int cna_fix_padding_bias_grad(const void* g, float* dres, int B, int H, int W, int C, int p, int dtype, void* stream);
 /* out = a * b elementwise (the gate and its gradients). */

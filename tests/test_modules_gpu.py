@@ -302,3 +302,58 @@ def test_msca_training_path_gradients_vs_autograd(form):
         assert p1.grad is not None, n1
         denom = p2.grad.norm().clamp_min(1e-6)
         assert (p1.grad.cpu() - p2.grad).norm() / denom < 2e-4, (n1, ((p1.grad.cpu() - p2.grad).norm() / denom).item())
+
+
+def test_msca_rep_exactness_at_full_mscan_t_size():
+    """BASELINE config 4 at full size (MSCAN-T stage 1: 32 channels, 128 x 128, batch 32): the exact re-parameterisations
+    (d0 + fix: merged 21x21 kernel; d4 + fix: four SVD cascades) reproduce the original block — a size-independent property that
+    needs no CPU oracle — in fp32, and the bf16 forms agree with the fp32 result to bf16 accuracy."""
+    from approx.core import MscaRep
+    from approx.layers import MSCA
+    torch.manual_seed(21)
+    src = MSCA(32, 5, (7, 11, 21))
+    x = torch.randn(32, 32, 128, 128, device="cuda")
+    with torch.no_grad():
+        y0 = src.cuda().eval()(x)
+        for d in (0, 4):
+            app = MscaRep(decomp=d, fix=True)
+            sub = app.initialize(src.cpu())
+            with contextlib.redirect_stdout(io.StringIO()):
+                app.optimize(sub)
+            tgt = app.postprocess(sub).cuda().eval()
+            assert O.compare4d(y0, tgt(x)) < 2e-5, d
+            yb = tgt.bfloat16()(x.bfloat16())
+            assert O.compare4d(y0, yb.float()) < 1e-2, d
+        src.cuda()
+
+
+@pytest.mark.parametrize("decomp", [False, True])
+def test_lowrank1_training_path_gradients_vs_autograd(decomp):
+    """LowRankExpConvV1 in model.train(): forward, input and parameter gradients of the CUDA path (grouped conv with channel
+    multiplier or its separable form, then the 1x1 mix) against torch autograd through stock convs on the CPU (exact fp32)."""
+    import copy
+    import torch.nn.functional as F
+    from approx.layers import LowRankExpConvV1
+    torch.manual_seed(17)
+    C, N, M, d = 12, 20, 4, 3
+    m = LowRankExpConvV1(C, N, d, 1, 1, num_base=M, decomp=decomp)
+    ref = copy.deepcopy(m)
+    m = m.cuda().train()
+    x = torch.randn(2, C, 11, 9)
+    gy = torch.randn(2, N, 11, 9)
+    x1 = x.clone().cuda().requires_grad_(True)
+    y1 = m(x1)
+    y1.backward(gy.cuda())
+    x2 = x.clone().requires_grad_(True)
+    if decomp:
+        t = F.conv2d(x2, ref.s_conv.v_conv.weight, None, 1, (1, 0), 1, C)
+        t = F.conv2d(t, ref.s_conv.h_conv.weight, None, 1, (0, 1), 1, C * M)
+    else:
+        t = F.conv2d(x2, ref.s_conv.weight, ref.s_conv.bias, 1, 1, 1, C)
+    y2 = F.conv2d(t, ref.d_conv.weight, ref.d_conv.bias)
+    y2.backward(gy)
+    assert O.compare4d(y2.detach(), y1.detach().cpu()) < 1e-5
+    assert (x1.grad.cpu() - x2.grad).norm() / x2.grad.norm() < 1e-4
+    for (n1, p1), (n2, p2) in zip(m.named_parameters(), ref.named_parameters()):
+        assert n1 == n2 and p1.grad is not None, n1
+        assert (p1.grad.cpu() - p2.grad).norm() / p2.grad.norm().clamp_min(1e-6) < 2e-4, n1

@@ -252,7 +252,6 @@ int cna_conv1x1_tc_forward(const void* a, const void* w_packed, const float* bia
                            int N, int relu, void* stream) {
     CNA_CHECK(a && w_packed && y && P > 0, "bad arguments");
     CNA_CHECK(cna_conv1x1_tc_supported(C, N), "configuration not supported (needs C%32==0, N%16==0, N<=256, W resident in smem)");
-    CNA_CHECK(gate == nullptr || N == C || true, "gate");
     CNA_CHECK(P < (1LL << 31) * 128LL, "too many pixels");
     static int num_sms = 0, max_smem = 0;
     if (num_sms == 0) {

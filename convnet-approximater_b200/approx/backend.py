@@ -30,6 +30,8 @@ _SIGS = {
     "cna_conv1x1_tc_supported": "ii",
     "cna_conv1x1_pack": "ppiip",
     "cna_conv1x1_tc_forward": "pppppLiiip",
+    "cna_lowrank1_fused_supported": "iiiiiiii",
+    "cna_lowrank1_fused_forward": "pppppiiiiiiiip",
     "cna_fix_padding_bias": "ppiiiiiip",
     "cna_add": "pppLip",
     "cna_lowrank2_pack": "ppppiiiiiip",
@@ -251,6 +253,42 @@ def conv1x1_tc(x, w_nc, bias, relu=False, gate=None):
         assert gate.shape == y.shape and gate.dtype == x.dtype and gate.is_contiguous()
     with torch.cuda.device(x.device):
         _check(lib().cna_conv1x1_tc_forward(_p(x), _p(w_nc), _p(bias), _p(gate), _p(y), Bn * H * W, C, N, int(relu), _stream(x)))
+    return y
+
+
+def lowrank1_fused_supported(B, H, W, C, N, M, d, separable) -> bool:
+    return bool(lib().cna_lowrank1_fused_supported(int(B), int(H), int(W), int(C), int(N), int(M), int(d), int(bool(separable))))
+
+
+def lowrank1_pack_s(s_conv, M: int) -> torch.Tensor:
+    """Basis filters of LowRankExpConvV1.s_conv in the per-chunk layout the fused scheme-1 kernel stages with one bulk copy:
+    fp32 [C*M/64][rows][64] with rows = d*d taps + bias (grouped d x d conv) or d v-taps + d h-taps (SeparableConv).  Values
+    are rounded through bf16 like every other bf16-path weight."""
+    r = lambda w: w.detach().to(torch.bfloat16).to(torch.float32)
+    if hasattr(s_conv, "v_conv"):
+        v, h = s_conv.v_conv.weight, s_conv.h_conv.weight
+        CM, d = v.shape[0], v.shape[2]
+        rows = torch.cat([r(v).reshape(CM // 64, 64, d), r(h).reshape(CM // 64, 64, d)], 2)
+    else:
+        w = s_conv.weight
+        CM, d = w.shape[0], w.shape[2]
+        b = s_conv.bias.detach().to(torch.float32) if s_conv.bias is not None else torch.zeros(CM, device=w.device)
+        rows = torch.cat([r(w).reshape(CM // 64, 64, d * d), b.reshape(CM // 64, 64, 1)], 2)
+    return rows.transpose(1, 2).contiguous()
+
+
+def lowrank1_fused(x, s_packed, dw_packed, d_bias, M: int, d: int, separable: bool):
+    """x (B,H,W,C) bf16 NHWC -> (B,H,W,N) bf16: d_conv(s_conv(x)) in one tcgen05 kernel (csrc/lowrank1_tc.cu)."""
+    _ready(x)
+    Bn, H, W, C = x.shape
+    N = dw_packed.shape[0]
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and dw_packed.dtype == torch.bfloat16
+    assert dw_packed.shape == (N, C * M) and dw_packed.is_contiguous() and s_packed.dtype == torch.float32 and s_packed.is_contiguous()
+    assert s_packed.shape == (C * M // 64, 2 * d if separable else d * d + 1, 64), tuple(s_packed.shape)
+    y = torch.empty((Bn, H, W, N), device=x.device, dtype=torch.bfloat16)
+    with torch.cuda.device(x.device):
+        _check(lib().cna_lowrank1_fused_forward(_p(x), _p(s_packed), _p(dw_packed), _p(d_bias), _p(y), Bn, H, W, C, N, int(M), int(d),
+                                                int(bool(separable)), _stream(x)))
     return y
 
 

@@ -63,7 +63,24 @@ class LowRankExpConvV1(nn.Module):
     def bias(self):
         return self.d_conv.bias
 
-    def forward_nhwc(self, x):
+    def _fused(self, x):
+        """One tcgen05 kernel for d_conv(s_conv(x)) (csrc/lowrank1_tc.cu) when the layer fits it: bf16, stride 1, 'same'."""
+        d = self.kernel_size[0]
+        sep = isinstance(self.s_conv, SeparableConv)
+        if not (x.dtype == torch.bfloat16 and x.is_contiguous() and self.kernel_size == (d, d) and self.stride == (1, 1)
+                and self.padding == (d // 2, d // 2) and (self.in_channels * self.num_base) % 64 == 0
+                and B.lowrank1_fused_supported(*x.shape[:3], self.in_channels, self.out_channels, self.num_base, d, sep)):
+            return None
+        params = tuple(self.s_conv.parameters())
+        sp = _ops.cached(self, "s_packed", params, torch.bfloat16, lambda: B.lowrank1_pack_s(self.s_conv, self.num_base))
+        dp = _ops.cached(self.d_conv, "w_1x1_tc", (self.d_conv.weight,), torch.bfloat16, lambda: B.conv1x1_pack(self.d_conv.weight))
+        return B.lowrank1_fused(x, sp, dp, _ops.bias_f32(self.d_conv), self.num_base, d, sep)
+
+    def forward_nhwc(self, x, fused=True):
+        if fused:
+            y = self._fused(x)
+            if y is not None:
+                return y
         t = self.s_conv.forward_nhwc(x) if isinstance(self.s_conv, SeparableConv) else _ops.dw(self.s_conv, x)
         return _ops.dense_taps(self.d_conv, t)
 

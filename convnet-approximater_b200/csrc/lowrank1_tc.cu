@@ -1,0 +1,502 @@
+// Fused scheme-1 low-rank convolution (Jaderberg et al. scheme 1) for bf16 NHWC tensors:
+//     y[p, n] = sum_{c,m} D[n, c*M+m] * s[p, c*M+m] + db[n]
+//     s[p, c*M+m] = bf16( sum_{i,j} x[p + (i,j), c] * w[c*M+m][i][j] + sb[c*M+m] )                     (d x d basis filters)
+//                 = bf16( sum_j h[c*M+m][j] * bf16( sum_i v[c*M+m][i] * x[p + (i,j), c] ) )             (after decomp())
+// Replaces LowRankExpConvV1.forward = d_conv(s_conv(x)) (reference src/approx/layers/low_rank_conv.py:44-52, SeparableConv
+// :17-25): the reference materialises the (B, C*M, H, W) intermediate — M times the input — between a grouped conv and a
+// 1x1 conv; here it only ever exists as 128 x 64 bf16 slabs in shared memory, produced by CUDA cores straight into the
+// UMMA A-operand layout and consumed by tcgen05 (the layer is tensor-bound once fused, AI ~ C*M*N/(C+N)).
+// The intermediate is rounded to bf16 exactly where the reference's bf16 modules materialise it.
+//
+//   tile     R = min(128 / W, H) full-width rows of the (B*H)-row image stack = up to 128 output pixels (M-tile rows
+//            m = r*W + w); a tile may straddle two images: each image segment gets its own zero-filled TMA halo box
+//   K-chunk  64 wide channels = 64/M input channels; per chunk the TMA warp stages the x halo box(es) (OOB zero fill = the
+//            conv padding) and that chunk's basis filters (+ bias) with one bulk copy
+//   warps    0: TMA producer (x + basis filters ring, D slab ring)   1: MMA issuer (TMEM owner)
+//            2-9: A producers — thread = (8 wide channels, 4 pixels): d*d (or separable d+d) taps in packed FFMA2, bf16 pack,
+//                 one 16-byte store into the no-swizzle K-major A buffer (plane pitch 2112 B: conflict-free)
+//            10-13: epilogue (TMEM -> + bias -> bf16 -> global)
+//   D slabs  bf16 [N][C*M] streamed as (NT x 64) slabs (two 64B-swizzled 32-wide halves) through a 3-4 deep ring;
+//            N <= 256: one N-tile and two TMEM accumulators; 256 < N <= 512: two N-tiles sharing every A slab
+#include "common.cuh"
+#include "ptx.cuh"
+
+#include <cuda.h>
+#include <algorithm>
+#include <mutex>
+
+namespace cna {
+using namespace ptx;
+
+constexpr int kL1ProdWarps = 8;
+constexpr int kL1ProdThreads = 32 * kL1ProdWarps;
+constexpr int kL1Threads = 32 * (2 + kL1ProdWarps + 4);
+constexpr int kL1SX = 3;                  // x / basis-filter staging ring
+constexpr int kL1SA = 2;                  // A slabs
+constexpr int kL1SWMax = 4;               // D slab ring (at most)
+constexpr uint32_t kL1ASbo = 128;         // A: no-swizzle K-major, 8-row groups of 16-byte rows
+constexpr uint32_t kL1ALbo = 2112;        // pitch between the 8 k-planes (2048 + 64: spreads the producer stores over all banks)
+constexpr uint32_t kL1ABytes = 8 * kL1ALbo;
+
+struct L1Params {
+    int B, H, W, C, N;
+    int R, G, ntiles, nchunks;            // rows per tile, B*H, tiles, K-chunks of 64 wide channels
+    int NT, nnt, nbuf, sw;                // N-tile width, N-tiles, TMEM accumulator buffers, D ring depth
+    int WP, RP, pad;                      // halo box: W + 2 pad columns, R + 2 pad rows
+    uint32_t seg_box_bytes, seg_bytes, wblk_bytes, xs_stage;
+    uint32_t off_xs, off_a, a_buf, off_w, w_sub, w_stage, off_bias, off_bar;
+};
+
+__host__ __device__ constexpr uint64_t l1_desc_hi(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+    return ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)(layout_type & 7) << 61);
+}
+
+__device__ __forceinline__ float2 l1_ffma2(float2 a, float2 b, float2 c) {      // SASS FFMA2
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                       rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float l1_lds_bf16(uint32_t addr) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return __uint_as_float((uint32_t)v << 16);
+}
+__device__ __forceinline__ void l1_lds_f8(uint32_t addr, float2 (&w)[4]) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w[0].x), "=f"(w[0].y), "=f"(w[1].x), "=f"(w[1].y) : "r"(addr));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w[2].x), "=f"(w[2].y), "=f"(w[3].x), "=f"(w[3].y) : "r"(addr + 16));
+}
+__device__ __forceinline__ void l1_sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void l1_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t l1_pack(float2 v) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(v.x, v.y);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float2 l1_round_bf16(float2 v) {
+    const uint32_t u = l1_pack(v);
+    return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+__device__ __forceinline__ void l1_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+enum : int {
+    L1_XS_FULL = 0, L1_XS_EMPTY = L1_XS_FULL + kL1SX, L1_A_FULL = L1_XS_EMPTY + kL1SX, L1_A_EMPTY = L1_A_FULL + kL1SA,
+    L1_W_FULL = L1_A_EMPTY + kL1SA, L1_W_EMPTY = L1_W_FULL + kL1SWMax, L1_ACC_FULL = L1_W_EMPTY + kL1SWMax,
+    L1_ACC_EMPTY = L1_ACC_FULL + 2, L1_COUNT = L1_ACC_EMPTY + 2
+};
+
+// D: basis filter size (d x d), M: bases per input channel (wide channel c*M+m), SEP: separable (d,1).(1,d) form
+template <int D, int M, bool SEP>
+__global__ void __launch_bounds__(kL1Threads, 1)
+lowrank1_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                      const float* __restrict__ s_packed, const float* __restrict__ d_bias, __nv_bfloat16* __restrict__ y,
+                      const L1Params p) {
+    constexpr int CPC = 64 / M;                  // input channels per K-chunk
+    constexpr int NCU = (M >= 8) ? 1 : 8 / M;    // input channels behind one 8-wide unit
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bars = base + p.off_bar;
+    auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+    float* sbias = reinterpret_cast<float*>(base_ptr + p.off_bias);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + p.off_bar + 8 * L1_COUNT);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tm_x); prefetch_tmap(&tm_w);
+        for (int i = 0; i < kL1SX; ++i) { mbar_init(bar(L1_XS_FULL + i), 1); mbar_init(bar(L1_XS_EMPTY + i), kL1ProdThreads); }
+        for (int i = 0; i < kL1SA; ++i) { mbar_init(bar(L1_A_FULL + i), kL1ProdThreads); mbar_init(bar(L1_A_EMPTY + i), 1); }
+        for (int i = 0; i < kL1SWMax; ++i) { mbar_init(bar(L1_W_FULL + i), 1); mbar_init(bar(L1_W_EMPTY + i), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar(L1_ACC_FULL + i), 1); mbar_init(bar(L1_ACC_EMPTY + i), 128); }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<512>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+    for (int i = threadIdx.x; i < p.N; i += kL1Threads) sbias[i] = d_bias ? d_bias[i] : 0.f;
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const int first = blockIdx.x, step = gridDim.x;
+    const int my_tiles = first < p.ntiles ? (p.ntiles - first + step - 1) / step : 0;
+
+    if (warp == 0) {
+        // ---------------- TMA producer: per chunk the x halo box(es) + basis filters, then the D slab of every N-tile ----------------
+        int xs = 0, ws = 0; uint32_t xph = 0, wph = 0;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int g0 = (first + it * step) * p.R;
+            const int b0 = g0 / p.H, h0 = g0 - b0 * p.H;
+            const int R1 = min(p.R, p.H - h0);
+            const bool two = (R1 < p.R) && (b0 + 1 < p.B);
+            for (int ch = 0; ch < p.nchunks; ++ch) {
+                mbar_wait(bar(L1_XS_EMPTY + xs), xph ^ 1u);
+                if (elect_one()) {
+                    const uint32_t dst = base + p.off_xs + xs * p.xs_stage;
+                    mbar_arrive_expect_tx(bar(L1_XS_FULL + xs), (two ? 2u : 1u) * p.seg_box_bytes + p.wblk_bytes);
+                    tma_load_4d(dst, &tm_x, bar(L1_XS_FULL + xs), ch * CPC, -p.pad, h0 - p.pad, b0);
+                    if (two) tma_load_4d(dst + p.seg_bytes, &tm_x, bar(L1_XS_FULL + xs), ch * CPC, -p.pad, -p.pad - R1, b0 + 1);
+                    l1_bulk_load(dst + 2 * p.seg_bytes, s_packed + (size_t)ch * (p.wblk_bytes / 4), p.wblk_bytes, bar(L1_XS_FULL + xs));
+                }
+                __syncwarp();
+                if (++xs == kL1SX) { xs = 0; xph ^= 1u; }
+                for (int nt = 0; nt < p.nnt; ++nt) {
+                    mbar_wait(bar(L1_W_EMPTY + ws), wph ^ 1u);
+                    if (elect_one()) {
+                        const uint32_t dst = base + p.off_w + ws * p.w_stage;
+                        mbar_arrive_expect_tx(bar(L1_W_FULL + ws), 2u * (uint32_t)p.NT * 64u);
+                        tma_load_2d(dst, &tm_w, bar(L1_W_FULL + ws), ch * 64, nt * p.NT);
+                        tma_load_2d(dst + p.w_sub, &tm_w, bar(L1_W_FULL + ws), ch * 64 + 32, nt * p.NT);
+                    }
+                    __syncwarp();
+                    if (++ws == p.sw) { ws = 0; wph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | (8u << 24);
+        constexpr uint64_t adsc = l1_desc_hi(kL1ALbo, kL1ASbo, 0);      // no swizzle, K-major
+        constexpr uint64_t bdsc = l1_desc_hi(16, 8 * 64, 4);            // 64-byte rows, 64B swizzle, K-major
+        int ab = 0, ws = 0; uint32_t aph = 0, wph = 0;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int buf = it % p.nbuf;
+            const uint32_t use = (uint32_t)(it / p.nbuf);
+            mbar_wait(bar(L1_ACC_EMPTY + buf), (use & 1u) ^ 1u);
+            tc_fence_after_sync();
+            for (int ch = 0; ch < p.nchunks; ++ch) {
+                mbar_wait(bar(L1_A_FULL + ab), aph);
+                tc_fence_after_sync();
+                const uint32_t a_addr = base + p.off_a + ab * p.a_buf;
+                for (int nt = 0; nt < p.nnt; ++nt) {
+                    mbar_wait(bar(L1_W_FULL + ws), wph);
+                    tc_fence_after_sync();
+                    const uint32_t w_addr = base + p.off_w + ws * p.w_stage;
+                    const uint32_t d = tmem + buf * 256 + nt * p.NT;
+                    if (elect_one()) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t a = adsc + ((a_addr + ks * 2 * kL1ALbo) >> 4);
+                            const uint64_t b = bdsc + ((w_addr + (ks >> 1) * p.w_sub + (ks & 1) * 32) >> 4);
+                            umma_bf16(d, a, b, idesc, (uint32_t)((ch | ks) != 0));
+                        }
+                        umma_commit(bar(L1_W_EMPTY + ws));
+                        if (nt == p.nnt - 1) {
+                            umma_commit(bar(L1_A_EMPTY + ab));
+                            if (ch == p.nchunks - 1) umma_commit(bar(L1_ACC_FULL + buf));
+                        }
+                    }
+                    __syncwarp();
+                    if (++ws == p.sw) { ws = 0; wph ^= 1u; }
+                }
+                if (++ab == kL1SA) { ab = 0; aph ^= 1u; }
+            }
+        }
+    } else if (warp < 2 + kL1ProdWarps) {
+        // ---------------- A producers ----------------
+        const int pt = threadIdx.x - 64;
+        const int u = pt & 7, pl = pt >> 3;
+        int rk[4], wk[4];
+        uint32_t xoff[4], aoff[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int m = pl + 32 * k;
+            rk[k] = m / p.W; wk[k] = m - rk[k] * p.W;
+            xoff[k] = (uint32_t)((rk[k] * p.WP + wk[k]) * CPC + (u * 8) / M) * 2u;
+            aoff[k] = (uint32_t)u * kL1ALbo + (uint32_t)(m >> 3) * kL1ASbo + (uint32_t)(m & 7) * 16u;
+        }
+        const uint32_t row_pitch = (uint32_t)p.WP * CPC * 2u;
+        int xs = 0, ab = 0; uint32_t xph = 0, aph = 0;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int g0 = (first + it * step) * p.R;
+            const int b0 = g0 / p.H, h0 = g0 - b0 * p.H;
+            const int R1 = min(p.R, p.H - h0);
+            bool valid[4];
+            uint32_t xo[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                valid[k] = (rk[k] < p.R) && (g0 + rk[k] < p.G);
+                xo[k] = xoff[k] + (rk[k] >= R1 ? p.seg_bytes : 0u);
+            }
+            for (int ch = 0; ch < p.nchunks; ++ch) {
+                const uint32_t stage = base + p.off_xs + xs * p.xs_stage;
+                const uint32_t wb = stage + 2 * p.seg_bytes + (uint32_t)u * 32u;     // this unit's 8 floats of every row
+                mbar_wait(bar(L1_XS_FULL + xs), xph);
+                float2 acc[4][4];
+                if constexpr (!SEP) {
+                    float2 bs[4];
+                    l1_lds_f8(wb + D * D * 256, bs);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc[k][q] = bs[q];
+#pragma unroll
+                    for (int i = 0; i < D; ++i) {
+#pragma unroll
+                        for (int j = 0; j < D; ++j) {
+                            float2 w[4];
+                            l1_lds_f8(wb + (i * D + j) * 256, w);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                if (!valid[k]) continue;
+                                const uint32_t xa = stage + xo[k] + i * row_pitch + j * (CPC * 2);
+                                float xv[NCU];
+#pragma unroll
+                                for (int c = 0; c < NCU; ++c) xv[c] = l1_lds_bf16(xa + 2 * c);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float x0 = xv[(2 * q) / M % NCU], x1 = xv[(2 * q + 1) / M % NCU];
+                                    acc[k][q] = l1_ffma2(make_float2(x0, x1), w[q], acc[k][q]);
+                                }
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc[k][q] = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int j = 0; j < D; ++j) {
+                        float2 t[4][4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) t[k][q] = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int i = 0; i < D; ++i) {
+                            float2 w[4];
+                            l1_lds_f8(wb + i * 256, w);                       // v taps: rows 0 .. D-1
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                if (!valid[k]) continue;
+                                const uint32_t xa = stage + xo[k] + i * row_pitch + j * (CPC * 2);
+                                float xv[NCU];
+#pragma unroll
+                                for (int c = 0; c < NCU; ++c) xv[c] = l1_lds_bf16(xa + 2 * c);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float x0 = xv[(2 * q) / M % NCU], x1 = xv[(2 * q + 1) / M % NCU];
+                                    t[k][q] = l1_ffma2(make_float2(x0, x1), w[q], t[k][q]);
+                                }
+                            }
+                        }
+                        float2 wh[4];
+                        l1_lds_f8(wb + (D + j) * 256, wh);                    // h taps: rows D .. 2D-1
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) acc[k][q] = l1_ffma2(l1_round_bf16(t[k][q]), wh[q], acc[k][q]);
+                    }
+                }
+                // x stage consumed (all reads above are complete: their values fed the FMAs)
+                mbar_arrive(bar(L1_XS_EMPTY + xs));
+                if (++xs == kL1SX) { xs = 0; xph ^= 1u; }
+                mbar_wait(bar(L1_A_EMPTY + ab), aph ^ 1u);
+                const uint32_t a_addr = base + p.off_a + ab * p.a_buf;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (valid[k]) l1_sts_v4(a_addr + aoff[k], l1_pack(acc[k][0]), l1_pack(acc[k][1]), l1_pack(acc[k][2]), l1_pack(acc[k][3]));
+                fence_proxy_async_smem();
+                mbar_arrive(bar(L1_A_FULL + ab));
+                if (++ab == kL1SA) { ab = 0; aph ^= 1u; }
+            }
+        }
+    } else {
+        // ---------------- epilogue: TMEM -> + bias -> bf16 -> global ----------------
+        const int lg = warp & 3;
+        const uint32_t lane_addr = (uint32_t)(lg * 32) << 16;
+        const int m = lg * 32 + lane;
+        const int r = m / p.W, w = m - r * p.W;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int buf = it % p.nbuf;
+            const uint32_t use = (uint32_t)(it / p.nbuf);
+            const int g0 = (first + it * step) * p.R;
+            const bool ok = (r < p.R) && (g0 + r < p.G);
+            __nv_bfloat16* yrow = y + ((long long)(g0 + r) * p.W + w) * p.N;
+            mbar_wait(bar(L1_ACC_FULL + buf), use & 1u);
+            tc_fence_after_sync();
+            for (int n0 = 0; n0 < p.N; n0 += 32) {
+                uint32_t v[32];
+                if (n0 + 32 <= p.N) {
+                    l1_tmem_ld32(tmem + buf * 256 + lane_addr + n0, v);
+                } else {   // N % 32 == 16
+                    tmem_ld16(tmem + buf * 256 + lane_addr + n0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+#pragma unroll
+                    for (int i = 16; i < 32; ++i) v[i] = 0;
+                }
+                tmem_ld_wait();
+                if (n0 + 32 >= p.N) {
+                    tc_fence_before_sync();
+                    mbar_arrive(bar(L1_ACC_EMPTY + buf));      // accumulator drained
+                }
+                if (!ok) continue;
+                const int nvalid = min(32, p.N - n0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (q * 8 >= nvalid) break;
+                    uint4 o;
+                    o.x = l1_pack(make_float2(__uint_as_float(v[q * 8 + 0]) + sbias[n0 + q * 8 + 0], __uint_as_float(v[q * 8 + 1]) + sbias[n0 + q * 8 + 1]));
+                    o.y = l1_pack(make_float2(__uint_as_float(v[q * 8 + 2]) + sbias[n0 + q * 8 + 2], __uint_as_float(v[q * 8 + 3]) + sbias[n0 + q * 8 + 3]));
+                    o.z = l1_pack(make_float2(__uint_as_float(v[q * 8 + 4]) + sbias[n0 + q * 8 + 4], __uint_as_float(v[q * 8 + 5]) + sbias[n0 + q * 8 + 5]));
+                    o.w = l1_pack(make_float2(__uint_as_float(v[q * 8 + 6]) + sbias[n0 + q * 8 + 6], __uint_as_float(v[q * 8 + 7]) + sbias[n0 + q * 8 + 7]));
+                    *(reinterpret_cast<uint4*>(yrow + n0) + q) = o;
+                }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc<512>(tmem);
+    }
+}
+
+typedef CUresult (*EncodeTiledFnL1)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFnL1 l1_get_encode() {
+    static EncodeTiledFnL1 fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFnL1>(f);
+    });
+    return fn;
+}
+static int l1_encode(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                     const cuuint32_t* box, CUtensorMapSwizzle swz) {
+    EncodeTiledFnL1 fn = l1_get_encode();
+    CNA_CHECK(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CNA_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return 0;
+}
+
+static uint32_t l1_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+// Fills the tile / shared-memory plan; returns the dynamic smem bytes (incl. alignment slack) or 0 when the layer is not covered.
+static size_t l1_plan(L1Params& p, int B, int H, int W, int C, int N, int M, int d, int separable, size_t limit) {
+    if (!(d == 3 || d == 5) || !(M == 4 || M == 8)) return 0;
+    if (B <= 0 || H <= 0 || W <= 0 || W > 128) return 0;
+    const int cpc = 64 / M;
+    if (C <= 0 || C % cpc != 0 || C % 8 != 0) return 0;
+    if (N < 16 || N % 16 != 0 || N > 512 || (N > 256 && N % 32 != 0)) return 0;
+    if ((long long)B * H > (1LL << 30)) return 0;
+    p.B = B; p.H = H; p.W = W; p.C = C; p.N = N;
+    p.pad = d / 2;
+    p.R = std::min(128 / W, H);
+    p.G = B * H;
+    p.ntiles = (p.G + p.R - 1) / p.R;
+    p.nchunks = C / cpc;
+    p.nnt = N > 256 ? 2 : 1;
+    p.NT = N / p.nnt;
+    p.nbuf = N <= 256 ? 2 : 1;
+    p.WP = W + 2 * p.pad; p.RP = p.R + 2 * p.pad;
+    if (p.WP > 256 || p.RP > 256) return 0;
+    p.seg_box_bytes = (uint32_t)(cpc * 2 * p.WP * p.RP);
+    p.seg_bytes = l1_up(p.seg_box_bytes, 128);
+    p.wblk_bytes = (uint32_t)((separable ? 2 * d : d * d + 1) * 64 * 4);
+    p.xs_stage = l1_up(2 * p.seg_bytes + p.wblk_bytes, 128);
+    p.a_buf = l1_up(kL1ABytes, 1024);
+    p.w_sub = (uint32_t)p.NT * 64;
+    p.w_stage = 2 * p.w_sub;
+    const uint32_t bias_bytes = l1_up((uint32_t)N * 4, 128);
+    const uint32_t fixed = l1_up(kL1SX * p.xs_stage, 1024) + kL1SA * p.a_buf + bias_bytes + 1024 /*barriers*/ + 1024 /*alignment*/;
+    int sw = kL1SWMax;
+    while (sw > 2 && (size_t)fixed + (size_t)sw * p.w_stage > limit) --sw;
+    if ((size_t)fixed + (size_t)sw * p.w_stage > limit) return 0;
+    p.sw = sw;
+    p.off_a = 0;
+    p.off_w = kL1SA * p.a_buf;
+    p.off_xs = p.off_w + sw * p.w_stage;
+    p.off_bias = p.off_xs + l1_up(kL1SX * p.xs_stage, 1024);
+    p.off_bar = p.off_bias + bias_bytes;
+    return (size_t)p.off_bar + 1024 + 1024;
+}
+
+template <int D, int M, bool SEP>
+static int l1_launch(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const float* s_packed, const float* d_bias, void* y,
+                     const L1Params& p, size_t smem, int grid, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        CNA_CUDA(cudaFuncSetAttribute(lowrank1_fused_kernel<D, M, SEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    lowrank1_fused_kernel<D, M, SEP><<<grid, kL1Threads, smem, st>>>(tm_x, tm_w, s_packed, d_bias, (__nv_bfloat16*)y, p);
+    CNA_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace cna
+
+using namespace cna;
+
+extern "C" {
+
+int cna_lowrank1_fused_supported(int B, int H, int W, int C, int N, int M, int d, int separable) {
+    L1Params p{};
+    return l1_plan(p, B, H, W, C, N, M, d, separable, 227 * 1024) != 0 ? 1 : 0;
+}
+
+int cna_lowrank1_fused_forward(const void* x, const float* s_packed, const void* dw_packed, const float* d_bias, void* y, int B, int H,
+                               int W, int C, int N, int M, int d, int separable, void* stream) {
+    CNA_CHECK(x && s_packed && dw_packed && y, "bad arguments");
+    L1Params p{};
+    const size_t smem = l1_plan(p, B, H, W, C, N, M, d, separable, 227 * 1024);
+    CNA_CHECK(smem != 0, "configuration not covered by the fused scheme-1 kernel (bf16, stride 1, 'same' padding, d in {3,5}, "
+                         "M in {4,8}, C*M % 64 == 0, C % 8 == 0, N % 16 == 0, N <= 512, W <= 128)");
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        CNA_CUDA(cudaGetDevice(&dev));
+        CNA_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    CUtensorMap tm_x, tm_w;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t str[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+        cuuint32_t box[4] = {(cuuint32_t)(64 / M), (cuuint32_t)p.WP, (cuuint32_t)p.RP, 1};
+        if (l1_encode(&tm_x, x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+    }
+    {
+        const cuuint64_t CM = (cuuint64_t)C * M;
+        cuuint64_t dims[2] = {CM, (cuuint64_t)N};
+        cuuint64_t str[1] = {CM * 2};
+        cuuint32_t box[2] = {32, (cuuint32_t)p.NT};
+        if (l1_encode(&tm_w, dw_packed, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    }
+    const int grid = std::min(p.ntiles, num_sms);
+    cudaStream_t st = as_stream(stream);
+#define CNA_L1_CASE(DD, MM)                                                                                            \
+    if (d == DD && M == MM)                                                                                            \
+        return separable ? l1_launch<DD, MM, true>(tm_x, tm_w, s_packed, d_bias, y, p, smem, grid, st)                 \
+                         : l1_launch<DD, MM, false>(tm_x, tm_w, s_packed, d_bias, y, p, smem, grid, st);
+    CNA_L1_CASE(3, 8)
+    CNA_L1_CASE(5, 8)
+    CNA_L1_CASE(3, 4)
+    CNA_L1_CASE(5, 4)
+#undef CNA_L1_CASE
+    CNA_FAIL("no kernel instance for this (d, M)");
+}
+
+}  // extern "C"

@@ -74,6 +74,23 @@ int cna_conv1x1_pack(const float* w_nc, void* packed, int N, int C, void* stream
 int cna_conv1x1_tc_forward(const void* a, const void* w_packed, const float* bias, const void* gate, void* y, long long P, int C,
                            int N, int relu, void* stream);
 
+/* ---- fused scheme-1 low-rank convolution (tcgen05) --------------------------------------------- */
+/* y = d_conv(s_conv(x)) in ONE kernel for bf16 NHWC tensors, stride 1, 'same' padding: the (B, C*M, H, W) intermediate of
+ * LowRankExpConvV1.forward (src/approx/layers/low_rank_conv.py:44-52; SeparableConv :17-25 after decomp()) is produced by CUDA
+ * cores 128 pixels x 64 wide channels at a time straight into the UMMA A-operand layout in shared memory, rounded to bf16 where
+ * the reference's bf16 modules materialise it, and consumed by tcgen05 against the streamed d_conv weight.
+ *   x         (B,H,W,C) bf16, dense
+ *   s_packed  fp32, per K-chunk of 64 wide channels (wide channel c*M+m):
+ *               separable == 0: [d*d taps (i*d+j)][64] basis filters then [64] s_conv bias      (s_conv = nn.Conv2d, groups=C)
+ *               separable == 1: [d v-taps][64] then [d h-taps][64]                                (SeparableConv, bias-free)
+ *   dw_packed bf16 [N][C*M] (cna_conv1x1_pack of d_conv.weight), d_bias fp32 (N,) or NULL
+ *   y         (B,H,W,N) bf16
+ * Covered: d in {3,5}, M in {4,8}, C*M % 64 == 0, C % 8 == 0, N % 16 == 0, N <= 512 (N % 32 == 0 above 256), W <= 128;
+ * everything else stays on cna_dwconv_forward + cna_conv1x1_tc_forward / cna_conv_taps_forward. */
+int cna_lowrank1_fused_supported(int B, int H, int W, int C, int N, int M, int d, int separable);
+int cna_lowrank1_fused_forward(const void* x, const float* s_packed, const void* dw_packed, const float* d_bias, void* y, int B, int H,
+                               int W, int C, int N, int M, int d, int separable, void* stream);
+
 /* ---- depthwise convolution (generic) -------------------------------------------------------- */
 /* Grouped conv with groups=Cin and channel multiplier `mult`: output channel co reads input channel co/mult.
  * w_packed[kh*kw][Cin*mult]; bias may be NULL.

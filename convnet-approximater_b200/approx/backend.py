@@ -274,7 +274,10 @@ def lowrank1_pack_s(s_conv, M: int) -> torch.Tensor:
         CM, d = w.shape[0], w.shape[2]
         b = s_conv.bias.detach().to(torch.float32) if s_conv.bias is not None else torch.zeros(CM, device=w.device)
         rows = torch.cat([r(w).reshape(CM // 64, 64, d * d), b.reshape(CM // 64, 64, 1)], 2)
-    return rows.transpose(1, 2).contiguous()
+    rows = rows.transpose(1, 2)                                             # [chunk][row][64 wide channels]
+    # within a row: unit u's channels 8u..8u+3 at floats [4u, 4u+4), channels 8u+4..8u+7 at [32+4u, 32+4u+4): a quarter-warp's
+    # 16-byte loads cover 128 contiguous bytes
+    return rows.reshape(rows.shape[0], rows.shape[1], 8, 2, 4).transpose(2, 3).reshape(rows.shape[0], rows.shape[1], 64).contiguous()
 
 
 def lowrank1_fused(x, s_packed, dw_packed, d_bias, M: int, d: int, separable: bool):

@@ -12,37 +12,41 @@
 //            m = r*W + w); a tile may straddle two images: each image segment gets its own zero-filled TMA halo box
 //   K-chunk  64 wide channels = 64/M input channels; per chunk the TMA warp stages the x halo box(es) (OOB zero fill = the
 //            conv padding) and that chunk's basis filters (+ bias) with one bulk copy
-//   warps    0: TMA producer (x + basis filters ring, D slab ring)   1: MMA issuer (TMEM owner)
-//            2-9: A producers — thread = (8 wide channels, 4 pixels): d*d (or separable d+d) taps in packed FFMA2, bf16 pack,
-//                 one 16-byte store into the no-swizzle K-major A buffer (plane pitch 2112 B: conflict-free)
-//            10-13: epilogue (TMEM -> + bias -> bf16 -> global)
-//   D slabs  bf16 [N][C*M] streamed as (NT x 64) slabs (two 64B-swizzled 32-wide halves) through a 3-4 deep ring;
+//   warps    0: TMA producer (x + basis filters ring)   1: MMA issuer (TMEM owner)   2: TMA producer (D slab ring)
+//            3-18: A producers, two groups of 8 warps on alternating chunks — thread = (8 wide channels, 4 pixels): d*d (or
+//                 separable d+d) taps in packed FFMA2 with immediate-offset shared loads, bf16 pack, one 16-byte store into the
+//                 128B-swizzled K-major A slab (the XOR pattern makes the stores conflict-free)
+//            19-22: epilogue (TMEM -> + bias -> bf16 -> global)
+//   D slabs  bf16 [N][C*M] streamed as (NT x 64) 128B-swizzled slabs through a ring of up to 8;
 //            N <= 256: one N-tile and two TMEM accumulators; 256 < N <= 512: two N-tiles sharing every A slab
 #include "common.cuh"
 #include "ptx.cuh"
 
 #include <cuda.h>
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
+#include <type_traits>
 
 namespace cna {
 using namespace ptx;
 
-constexpr int kL1ProdWarps = 8;
-constexpr int kL1ProdThreads = 32 * kL1ProdWarps;
-constexpr int kL1Threads = 32 * (2 + kL1ProdWarps + 4);
-constexpr int kL1SX = 3;                  // x / basis-filter staging ring
-constexpr int kL1SA = 2;                  // A slabs
-constexpr int kL1SWMax = 4;               // D slab ring (at most)
-constexpr uint32_t kL1ASbo = 128;         // A: no-swizzle K-major, 8-row groups of 16-byte rows
-constexpr uint32_t kL1ALbo = 2112;        // pitch between the 8 k-planes (2048 + 64: spreads the producer stores over all banks)
-constexpr uint32_t kL1ABytes = 8 * kL1ALbo;
+constexpr int kL1Groups = 2;               // producer groups: group g builds the A slabs of chunks q with q % 2 == g
+constexpr int kL1GroupThreads = 256;       // 8 warps per group: thread = (8 wide channels, 4 pixels)
+constexpr int kL1ProdWarps = kL1Groups * kL1GroupThreads / 32;
+constexpr int kL1Threads = 32 * (3 + kL1ProdWarps + 4);
+constexpr int kL1SXMax = 8;               // x / basis-filter staging ring (at most; depth chosen by the smem plan)
+constexpr int kL1SA = 2;                  // A slabs (one per producer group)
+constexpr int kL1SWMax = 8;               // D slab ring (at most)
+constexpr uint32_t kL1ABytes = 128 * 128;  // A slab: 128 pixels x 64 wide channels bf16, K-major rows of 128 bytes, 128B swizzle
 
 struct L1Params {
     int B, H, W, C, N;
     int R, G, ntiles, nchunks;            // rows per tile, B*H, tiles, K-chunks of 64 wide channels
-    int NT, nnt, nbuf, sw;                // N-tile width, N-tiles, TMEM accumulator buffers, D ring depth
+    int NT, nnt, nbuf, sw, sx;            // N-tile width, N-tiles, TMEM accumulator buffers, D ring depth, x ring depth
     int WP, RP, pad;                      // halo box: W + 2 pad columns, R + 2 pad rows
+    int debug;                            // CNA_L1_DEBUG ablations: 1 no taps, 2 no UMMAs, 8 no x loads, 16 no D loads
+    long long* prof;                      // CNA_L1_PROF: per-role wait/work cycle counters of CTA 0 (debugging aid), else NULL
     uint32_t seg_box_bytes, seg_bytes, wblk_bytes, xs_stage;
     uint32_t off_xs, off_a, a_buf, off_w, w_sub, w_stage, off_bias, off_bar;
 };
@@ -58,14 +62,25 @@ __device__ __forceinline__ float2 l1_ffma2(float2 a, float2 b, float2 c) {      
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
     return *reinterpret_cast<float2*>(&rd);
 }
+// compile-time loop: the tap indices become immediate offsets of the shared-memory loads
+template <int I, int N, typename F>
+__device__ __forceinline__ void l1_static_for(F&& f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        l1_static_for<I + 1, N>(f);
+    }
+}
+template <int IMM>
 __device__ __forceinline__ float l1_lds_bf16(uint32_t addr) {
     unsigned short v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    asm volatile("ld.shared.u16 %0, [%1+%2];" : "=h"(v) : "r"(addr), "n"(IMM));
     return __uint_as_float((uint32_t)v << 16);
 }
+// one row of basis-filter taps for this thread's 8 wide channels: floats [0,4) at +0, [4,8) at +128 (conflict-free layout)
+template <int IMM>
 __device__ __forceinline__ void l1_lds_f8(uint32_t addr, float2 (&w)[4]) {
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w[0].x), "=f"(w[0].y), "=f"(w[1].x), "=f"(w[1].y) : "r"(addr));
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w[2].x), "=f"(w[2].y), "=f"(w[3].x), "=f"(w[3].y) : "r"(addr + 16));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(w[0].x), "=f"(w[0].y), "=f"(w[1].x), "=f"(w[1].y) : "r"(addr), "n"(IMM));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(w[2].x), "=f"(w[2].y), "=f"(w[3].x), "=f"(w[3].y) : "r"(addr), "n"(IMM + 128));
 }
 __device__ __forceinline__ void l1_sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -96,9 +111,16 @@ __device__ __forceinline__ void l1_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) 
 }
 
 enum : int {
-    L1_XS_FULL = 0, L1_XS_EMPTY = L1_XS_FULL + kL1SX, L1_A_FULL = L1_XS_EMPTY + kL1SX, L1_A_EMPTY = L1_A_FULL + kL1SA,
+    L1_XS_FULL = 0, L1_XS_EMPTY = L1_XS_FULL + kL1SXMax, L1_A_FULL = L1_XS_EMPTY + kL1SXMax, L1_A_EMPTY = L1_A_FULL + kL1SA,
     L1_W_FULL = L1_A_EMPTY + kL1SA, L1_W_EMPTY = L1_W_FULL + kL1SWMax, L1_ACC_FULL = L1_W_EMPTY + kL1SWMax,
     L1_ACC_EMPTY = L1_ACC_FULL + 2, L1_COUNT = L1_ACC_EMPTY + 2
+};
+
+// profiling aid: cycles one thread of each role spends in each phase, CTA 0 only
+struct L1Prof {
+    long long* out; long long t; bool on;
+    __device__ __forceinline__ L1Prof(long long* o, bool sel) : out(o), t(0), on(o != nullptr && sel && blockIdx.x == 0) { if (on) t = clock64(); }
+    __device__ __forceinline__ void lap(int slot) { if (on) { const long long n = clock64(); atomicAdd((unsigned long long*)(out + slot), (unsigned long long)(n - t)); t = n; } }
 };
 
 // D: basis filter size (d x d), M: bases per input channel (wide channel c*M+m), SEP: separable (d,1).(1,d) form
@@ -120,8 +142,8 @@ lowrank1_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tm_x); prefetch_tmap(&tm_w);
-        for (int i = 0; i < kL1SX; ++i) { mbar_init(bar(L1_XS_FULL + i), 1); mbar_init(bar(L1_XS_EMPTY + i), kL1ProdThreads); }
-        for (int i = 0; i < kL1SA; ++i) { mbar_init(bar(L1_A_FULL + i), kL1ProdThreads); mbar_init(bar(L1_A_EMPTY + i), 1); }
+        for (int i = 0; i < kL1SXMax; ++i) { mbar_init(bar(L1_XS_FULL + i), 1); mbar_init(bar(L1_XS_EMPTY + i), kL1GroupThreads); }
+        for (int i = 0; i < kL1SA; ++i) { mbar_init(bar(L1_A_FULL + i), kL1GroupThreads); mbar_init(bar(L1_A_EMPTY + i), 1); }
         for (int i = 0; i < kL1SWMax; ++i) { mbar_init(bar(L1_W_FULL + i), 1); mbar_init(bar(L1_W_EMPTY + i), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(bar(L1_ACC_FULL + i), 1); mbar_init(bar(L1_ACC_EMPTY + i), 128); }
         fence_mbar_init();
@@ -136,31 +158,48 @@ lowrank1_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     const int my_tiles = first < p.ntiles ? (p.ntiles - first + step - 1) / step : 0;
 
     if (warp == 0) {
-        // ---------------- TMA producer: per chunk the x halo box(es) + basis filters, then the D slab of every N-tile ----------------
-        int xs = 0, ws = 0; uint32_t xph = 0, wph = 0;
+        // ---------------- TMA producer 1: per chunk the x halo box(es) + that chunk's basis filters ----------------
+        int xs = 0; uint32_t xph = 0;
+        L1Prof pf(p.prof, lane == 0);
         for (int it = 0; it < my_tiles; ++it) {
             const int g0 = (first + it * step) * p.R;
             const int b0 = g0 / p.H, h0 = g0 - b0 * p.H;
             const int R1 = min(p.R, p.H - h0);
             const bool two = (R1 < p.R) && (b0 + 1 < p.B);
             for (int ch = 0; ch < p.nchunks; ++ch) {
+                pf.lap(0);
                 mbar_wait(bar(L1_XS_EMPTY + xs), xph ^ 1u);
+                pf.lap(1);
                 if (elect_one()) {
                     const uint32_t dst = base + p.off_xs + xs * p.xs_stage;
-                    mbar_arrive_expect_tx(bar(L1_XS_FULL + xs), (two ? 2u : 1u) * p.seg_box_bytes + p.wblk_bytes);
-                    tma_load_4d(dst, &tm_x, bar(L1_XS_FULL + xs), ch * CPC, -p.pad, h0 - p.pad, b0);
-                    if (two) tma_load_4d(dst + p.seg_bytes, &tm_x, bar(L1_XS_FULL + xs), ch * CPC, -p.pad, -p.pad - R1, b0 + 1);
+                    const bool skip_x = (p.debug & 8) != 0;
+                    mbar_arrive_expect_tx(bar(L1_XS_FULL + xs), (skip_x ? 0u : (two ? 2u : 1u) * p.seg_box_bytes) + p.wblk_bytes);
+                    if (!skip_x) tma_load_4d(dst, &tm_x, bar(L1_XS_FULL + xs), ch * CPC, -p.pad, h0 - p.pad, b0);
+                    if (two && !skip_x) tma_load_4d(dst + p.seg_bytes, &tm_x, bar(L1_XS_FULL + xs), ch * CPC, -p.pad, -p.pad - R1, b0 + 1);
                     l1_bulk_load(dst + 2 * p.seg_bytes, s_packed + (size_t)ch * (p.wblk_bytes / 4), p.wblk_bytes, bar(L1_XS_FULL + xs));
                 }
                 __syncwarp();
-                if (++xs == kL1SX) { xs = 0; xph ^= 1u; }
+                if (++xs == p.sx) { xs = 0; xph ^= 1u; }
+            }
+        }
+    } else if (warp == 2) {
+        // ---------------- TMA producer 2: the D slab of every (chunk, N-tile), its own ring so neither stream stalls the other ----------------
+        int ws = 0; uint32_t wph = 0;
+        L1Prof pf(p.prof, lane == 0);
+        for (int it = 0; it < my_tiles; ++it) {
+            for (int ch = 0; ch < p.nchunks; ++ch) {
                 for (int nt = 0; nt < p.nnt; ++nt) {
+                    pf.lap(20);
                     mbar_wait(bar(L1_W_EMPTY + ws), wph ^ 1u);
+                    pf.lap(2);
                     if (elect_one()) {
                         const uint32_t dst = base + p.off_w + ws * p.w_stage;
-                        mbar_arrive_expect_tx(bar(L1_W_FULL + ws), 2u * (uint32_t)p.NT * 64u);
-                        tma_load_2d(dst, &tm_w, bar(L1_W_FULL + ws), ch * 64, nt * p.NT);
-                        tma_load_2d(dst + p.w_sub, &tm_w, bar(L1_W_FULL + ws), ch * 64 + 32, nt * p.NT);
+                        if (p.debug & 16) {
+                            mbar_arrive(bar(L1_W_FULL + ws));
+                        } else {
+                            mbar_arrive_expect_tx(bar(L1_W_FULL + ws), (uint32_t)p.NT * 128u);
+                            tma_load_2d(dst, &tm_w, bar(L1_W_FULL + ws), ch * 64, nt * p.NT);
+                        }
                     }
                     __syncwarp();
                     if (++ws == p.sw) { ws = 0; wph ^= 1u; }
@@ -170,29 +209,36 @@ lowrank1_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     } else if (warp == 1) {
         // ---------------- MMA issuer ----------------
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | (8u << 24);
-        constexpr uint64_t adsc = l1_desc_hi(kL1ALbo, kL1ASbo, 0);      // no swizzle, K-major
-        constexpr uint64_t bdsc = l1_desc_hi(16, 8 * 64, 4);            // 64-byte rows, 64B swizzle, K-major
+        constexpr uint64_t adsc = l1_desc_hi(16, 8 * 128, 2);           // 128-byte rows, 128B swizzle, K-major (written by the producers)
+        constexpr uint64_t bdsc = l1_desc_hi(16, 8 * 128, 2);           // 128-byte rows, 128B swizzle, K-major
         int ab = 0, ws = 0; uint32_t aph = 0, wph = 0;
+        L1Prof pf(p.prof, lane == 0);
         for (int it = 0; it < my_tiles; ++it) {
             const int buf = it % p.nbuf;
             const uint32_t use = (uint32_t)(it / p.nbuf);
+            pf.lap(17);
             mbar_wait(bar(L1_ACC_EMPTY + buf), (use & 1u) ^ 1u);
+            pf.lap(3);
             tc_fence_after_sync();
             for (int ch = 0; ch < p.nchunks; ++ch) {
+                pf.lap(17);
                 mbar_wait(bar(L1_A_FULL + ab), aph);
+                pf.lap(4);
                 tc_fence_after_sync();
                 const uint32_t a_addr = base + p.off_a + ab * p.a_buf;
                 for (int nt = 0; nt < p.nnt; ++nt) {
+                    pf.lap(17);
                     mbar_wait(bar(L1_W_FULL + ws), wph);
+                    pf.lap(5);
                     tc_fence_after_sync();
                     const uint32_t w_addr = base + p.off_w + ws * p.w_stage;
                     const uint32_t d = tmem + buf * 256 + nt * p.NT;
                     if (elect_one()) {
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
-                            const uint64_t a = adsc + ((a_addr + ks * 2 * kL1ALbo) >> 4);
-                            const uint64_t b = bdsc + ((w_addr + (ks >> 1) * p.w_sub + (ks & 1) * 32) >> 4);
-                            umma_bf16(d, a, b, idesc, (uint32_t)((ch | ks) != 0));
+                            const uint64_t a = adsc + ((a_addr + ks * 32) >> 4);
+                            const uint64_t b = bdsc + ((w_addr + ks * 32) >> 4);
+                            if (!(p.debug & 2)) umma_bf16(d, a, b, idesc, (uint32_t)((ch | ks) != 0));
                         }
                         umma_commit(bar(L1_W_EMPTY + ws));
                         if (nt == p.nnt - 1) {
@@ -206,21 +252,27 @@ lowrank1_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 if (++ab == kL1SA) { ab = 0; aph ^= 1u; }
             }
         }
-    } else if (warp < 2 + kL1ProdWarps) {
-        // ---------------- A producers ----------------
-        const int pt = threadIdx.x - 64;
+    } else if (warp < 3 + kL1ProdWarps) {
+        // ---------------- A producers: two groups of 8 warps on alternating chunks ----------------
+        const int grp = (warp - 3) >> 3;
+        const int pt = threadIdx.x - 96 - grp * kL1GroupThreads;
         const int u = pt & 7, pl = pt >> 3;
-        int rk[4], wk[4];
+        int rk[4];
         uint32_t xoff[4], aoff[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int m = pl + 32 * k;
-            rk[k] = m / p.W; wk[k] = m - rk[k] * p.W;
-            xoff[k] = (uint32_t)((rk[k] * p.WP + wk[k]) * CPC + (u * 8) / M) * 2u;
-            aoff[k] = (uint32_t)u * kL1ALbo + (uint32_t)(m >> 3) * kL1ASbo + (uint32_t)(m & 7) * 16u;
+            rk[k] = m / p.W;
+            const int wk = m - rk[k] * p.W;
+            // slots past the tile (rk >= R) compute on slot 0's data and are never stored
+            xoff[k] = rk[k] < p.R ? (uint32_t)((rk[k] * p.WP + wk) * CPC + (u * 8) / M) * 2u : (uint32_t)((u * 8) / M) * 2u;
+            aoff[k] = (uint32_t)m * 128u + (uint32_t)((u ^ (m & 7)) * 16);      // 128B swizzle: 16-byte unit u of row m lands at u ^ (m % 8)
         }
         const uint32_t row_pitch = (uint32_t)p.WP * CPC * 2u;
-        int xs = 0, ab = 0; uint32_t xph = 0, aph = 0;
+        const uint32_t a_addr = base + p.off_a + grp * p.a_buf;
+        uint32_t q = 0;                                   // chunk counter over this CTA's tiles
+        L1Prof pf(p.prof, pt == 0);
+        const int pslot = 6 + 6 * grp;                   // 6.. group 0, 12.. group 1 : XS_FULL wait, taps, A_EMPTY wait, store
         for (int it = 0; it < my_tiles; ++it) {
             const int g0 = (first + it * step) * p.R;
             const int b0 = g0 / p.H, h0 = g0 - b0 * p.H;
@@ -230,90 +282,119 @@ lowrank1_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 valid[k] = (rk[k] < p.R) && (g0 + rk[k] < p.G);
-                xo[k] = xoff[k] + (rk[k] >= R1 ? p.seg_bytes : 0u);
+                xo[k] = xoff[k] + ((rk[k] >= R1 && rk[k] < p.R) ? p.seg_bytes : 0u);
             }
-            for (int ch = 0; ch < p.nchunks; ++ch) {
+            for (int ch = 0; ch < p.nchunks; ++ch, ++q) {
+                if ((int)(q & 1u) != grp) continue;
+                const uint32_t xs = q % (uint32_t)p.sx, xph = (q / (uint32_t)p.sx) & 1u, aph = (q >> 1) & 1u;
                 const uint32_t stage = base + p.off_xs + xs * p.xs_stage;
-                const uint32_t wb = stage + 2 * p.seg_bytes + (uint32_t)u * 32u;     // this unit's 8 floats of every row
+                const uint32_t wb = stage + 2 * p.seg_bytes + (uint32_t)u * 16u;     // this unit's floats of every tap row
+                pf.lap(pslot + 4);
                 mbar_wait(bar(L1_XS_FULL + xs), xph);
-                float2 acc[4][4];
+                pf.lap(pslot);
+                uint32_t pk[4][4];
+                uint32_t xr[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) xr[k] = stage + xo[k];
                 if constexpr (!SEP) {
+                    float2 acc[4][4];
                     float2 bs[4];
-                    l1_lds_f8(wb + D * D * 256, bs);
+                    l1_lds_f8<D * D * 256>(wb, bs);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) acc[k][q] = bs[q];
+                        for (int e = 0; e < 4; ++e) acc[k][e] = bs[e];
+                    if (!(p.debug & 1)) {
+                        l1_static_for<0, D>([&](auto ic) {
+                            constexpr int i = decltype(ic)::value;
+                            l1_static_for<0, D>([&](auto jc) {
+                                constexpr int j = decltype(jc)::value;
+                                float2 w[4];
+                                l1_lds_f8<(i * D + j) * 256>(wb, w);
 #pragma unroll
-                    for (int i = 0; i < D; ++i) {
+                                for (int k = 0; k < 4; ++k) {
+                                    float xv[NCU];
+                                    l1_static_for<0, NCU>([&](auto cc) {
+                                        constexpr int c = decltype(cc)::value;
+                                        xv[c] = l1_lds_bf16<j * (CPC * 2) + 2 * c>(xr[k]);
+                                    });
 #pragma unroll
-                        for (int j = 0; j < D; ++j) {
-                            float2 w[4];
-                            l1_lds_f8(wb + (i * D + j) * 256, w);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                if (!valid[k]) continue;
-                                const uint32_t xa = stage + xo[k] + i * row_pitch + j * (CPC * 2);
-                                float xv[NCU];
-#pragma unroll
-                                for (int c = 0; c < NCU; ++c) xv[c] = l1_lds_bf16(xa + 2 * c);
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    const float x0 = xv[(2 * q) / M % NCU], x1 = xv[(2 * q + 1) / M % NCU];
-                                    acc[k][q] = l1_ffma2(make_float2(x0, x1), w[q], acc[k][q]);
+                                    for (int e = 0; e < 4; ++e) {
+                                        const float x0 = xv[(2 * e) / M % NCU], x1 = xv[(2 * e + 1) / M % NCU];
+                                        acc[k][e] = l1_ffma2(make_float2(x0, x1), w[e], acc[k][e]);
+                                    }
                                 }
-                            }
-                        }
+                            });
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) xr[k] += row_pitch;
+                        });
                     }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) pk[k][e] = l1_pack(acc[k][e]);
                 } else {
+                    // two pixels at a time: keeps the column accumulators t and the outputs within the register budget
+                    l1_static_for<0, 2>([&](auto kc) {
+                        constexpr int kp = decltype(kc)::value;
+                        float2 acc[2][4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
+                        for (int kk = 0; kk < 2; ++kk)
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) acc[k][q] = make_float2(0.f, 0.f);
+                            for (int e = 0; e < 4; ++e) acc[kk][e] = make_float2(0.f, 0.f);
+                        if (!(p.debug & 1)) {
+                            l1_static_for<0, D>([&](auto jc) {
+                                constexpr int j = decltype(jc)::value;
+                                float2 t[2][4];
 #pragma unroll
-                    for (int j = 0; j < D; ++j) {
-                        float2 t[4][4];
+                                for (int kk = 0; kk < 2; ++kk)
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
+                                    for (int e = 0; e < 4; ++e) t[kk][e] = make_float2(0.f, 0.f);
+                                uint32_t xc[2] = {xr[2 * kp], xr[2 * kp + 1]};
+                                l1_static_for<0, D>([&](auto ic) {
+                                    constexpr int i = decltype(ic)::value;
+                                    float2 w[4];
+                                    l1_lds_f8<i * 256>(wb, w);                        // v taps: rows 0 .. D-1
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) t[k][q] = make_float2(0.f, 0.f);
+                                    for (int kk = 0; kk < 2; ++kk) {
+                                        float xv[NCU];
+                                        l1_static_for<0, NCU>([&](auto cc) {
+                                            constexpr int c = decltype(cc)::value;
+                                            xv[c] = l1_lds_bf16<j * (CPC * 2) + 2 * c>(xc[kk]);
+                                        });
 #pragma unroll
-                        for (int i = 0; i < D; ++i) {
-                            float2 w[4];
-                            l1_lds_f8(wb + i * 256, w);                       // v taps: rows 0 .. D-1
+                                        for (int e = 0; e < 4; ++e) {
+                                            const float x0 = xv[(2 * e) / M % NCU], x1 = xv[(2 * e + 1) / M % NCU];
+                                            t[kk][e] = l1_ffma2(make_float2(x0, x1), w[e], t[kk][e]);
+                                        }
+                                        xc[kk] += row_pitch;
+                                    }
+                                });
+                                float2 wh[4];
+                                l1_lds_f8<(D + j) * 256>(wb, wh);                     // h taps: rows D .. 2D-1
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                if (!valid[k]) continue;
-                                const uint32_t xa = stage + xo[k] + i * row_pitch + j * (CPC * 2);
-                                float xv[NCU];
+                                for (int kk = 0; kk < 2; ++kk)
 #pragma unroll
-                                for (int c = 0; c < NCU; ++c) xv[c] = l1_lds_bf16(xa + 2 * c);
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    const float x0 = xv[(2 * q) / M % NCU], x1 = xv[(2 * q + 1) / M % NCU];
-                                    t[k][q] = l1_ffma2(make_float2(x0, x1), w[q], t[k][q]);
-                                }
-                            }
+                                    for (int e = 0; e < 4; ++e) acc[kk][e] = l1_ffma2(l1_round_bf16(t[kk][e]), wh[e], acc[kk][e]);
+                            });
                         }
-                        float2 wh[4];
-                        l1_lds_f8(wb + (D + j) * 256, wh);                    // h taps: rows D .. 2D-1
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
+                        for (int kk = 0; kk < 2; ++kk)
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) acc[k][q] = l1_ffma2(l1_round_bf16(t[k][q]), wh[q], acc[k][q]);
-                    }
+                            for (int e = 0; e < 4; ++e) pk[2 * kp + kk][e] = l1_pack(acc[kk][e]);
+                    });
                 }
-                // x stage consumed (all reads above are complete: their values fed the FMAs)
+                // x stage consumed (the loads above have returned: their values fed the FMAs)
                 mbar_arrive(bar(L1_XS_EMPTY + xs));
-                if (++xs == kL1SX) { xs = 0; xph ^= 1u; }
-                mbar_wait(bar(L1_A_EMPTY + ab), aph ^ 1u);
-                const uint32_t a_addr = base + p.off_a + ab * p.a_buf;
+                pf.lap(pslot + 1);
+                mbar_wait(bar(L1_A_EMPTY + grp), aph ^ 1u);
+                pf.lap(pslot + 2);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    if (valid[k]) l1_sts_v4(a_addr + aoff[k], l1_pack(acc[k][0]), l1_pack(acc[k][1]), l1_pack(acc[k][2]), l1_pack(acc[k][3]));
+                    if (valid[k]) l1_sts_v4(a_addr + aoff[k], pk[k][0], pk[k][1], pk[k][2], pk[k][3]);
                 fence_proxy_async_smem();
-                mbar_arrive(bar(L1_A_FULL + ab));
-                if (++ab == kL1SA) { ab = 0; aph ^= 1u; }
+                mbar_arrive(bar(L1_A_FULL + grp));
+                pf.lap(pslot + 3);
             }
         }
     } else {
@@ -322,13 +403,16 @@ lowrank1_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         const uint32_t lane_addr = (uint32_t)(lg * 32) << 16;
         const int m = lg * 32 + lane;
         const int r = m / p.W, w = m - r * p.W;
+        L1Prof pf(p.prof, m == 0);
         for (int it = 0; it < my_tiles; ++it) {
             const int buf = it % p.nbuf;
             const uint32_t use = (uint32_t)(it / p.nbuf);
             const int g0 = (first + it * step) * p.R;
             const bool ok = (r < p.R) && (g0 + r < p.G);
             __nv_bfloat16* yrow = y + ((long long)(g0 + r) * p.W + w) * p.N;
+            pf.lap(19);
             mbar_wait(bar(L1_ACC_FULL + buf), use & 1u);
+            pf.lap(18);
             tc_fence_after_sync();
             for (int n0 = 0; n0 < p.N; n0 += 32) {
                 uint32_t v[32];
@@ -419,17 +503,23 @@ static size_t l1_plan(L1Params& p, int B, int H, int W, int C, int N, int M, int
     p.xs_stage = l1_up(2 * p.seg_bytes + p.wblk_bytes, 128);
     p.a_buf = l1_up(kL1ABytes, 1024);
     p.w_sub = (uint32_t)p.NT * 64;
-    p.w_stage = 2 * p.w_sub;
+    p.w_stage = (uint32_t)p.NT * 128;
     const uint32_t bias_bytes = l1_up((uint32_t)N * 4, 128);
-    const uint32_t fixed = l1_up(kL1SX * p.xs_stage, 1024) + kL1SA * p.a_buf + bias_bytes + 1024 /*barriers*/ + 1024 /*alignment*/;
-    int sw = kL1SWMax;
-    while (sw > 2 && (size_t)fixed + (size_t)sw * p.w_stage > limit) --sw;
-    if ((size_t)fixed + (size_t)sw * p.w_stage > limit) return 0;
-    p.sw = sw;
+    const uint32_t fixed = kL1SA * p.a_buf + bias_bytes + 1024 /*barriers*/ + 1024 /*alignment*/ + 1024 /*x ring round-up*/;
+    // ring depths: as many chunks of look-ahead as shared memory allows, balanced between the two streams (their latency, not
+    // their bandwidth, is what a shallow ring exposes)
+    int sw = std::min(kL1SWMax, 4 * p.nnt), sx = 6;
+    while ((size_t)fixed + (size_t)sw * p.w_stage + (size_t)sx * p.xs_stage > limit) {
+        if (sx > 2 && sx * p.nnt >= sw) --sx;
+        else if (sw > 2) --sw;
+        else if (sx > 2) --sx;
+        else return 0;
+    }
+    p.sw = sw; p.sx = sx;
     p.off_a = 0;
     p.off_w = kL1SA * p.a_buf;
     p.off_xs = p.off_w + sw * p.w_stage;
-    p.off_bias = p.off_xs + l1_up(kL1SX * p.xs_stage, 1024);
+    p.off_bias = p.off_xs + l1_up(sx * p.xs_stage, 1024);
     p.off_bar = p.off_bias + bias_bytes;
     return (size_t)p.off_bar + 1024 + 1024;
 }
@@ -482,21 +572,45 @@ int cna_lowrank1_fused_forward(const void* x, const float* s_packed, const void*
         const cuuint64_t CM = (cuuint64_t)C * M;
         cuuint64_t dims[2] = {CM, (cuuint64_t)N};
         cuuint64_t str[1] = {CM * 2};
-        cuuint32_t box[2] = {32, (cuuint32_t)p.NT};
-        if (l1_encode(&tm_w, dw_packed, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+        cuuint32_t box[2] = {64, (cuuint32_t)p.NT};
+        if (l1_encode(&tm_w, dw_packed, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     }
     const int grid = std::min(p.ntiles, num_sms);
     cudaStream_t st = as_stream(stream);
+    static const int debug = [] { const char* e = getenv("CNA_L1_DEBUG"); return e ? atoi(e) : 0; }();
+    p.debug = debug;
+    static const bool prof_on = getenv("CNA_L1_PROF") != nullptr;
+    static long long* prof_dev = nullptr;
+    if (prof_on) {
+        if (!prof_dev) CNA_CUDA(cudaMalloc(&prof_dev, 32 * sizeof(long long)));
+        CNA_CUDA(cudaMemsetAsync(prof_dev, 0, 32 * sizeof(long long), st));
+        p.prof = prof_dev;
+    }
 #define CNA_L1_CASE(DD, MM)                                                                                            \
     if (d == DD && M == MM)                                                                                            \
-        return separable ? l1_launch<DD, MM, true>(tm_x, tm_w, s_packed, d_bias, y, p, smem, grid, st)                 \
-                         : l1_launch<DD, MM, false>(tm_x, tm_w, s_packed, d_bias, y, p, smem, grid, st);
+        rc = separable ? l1_launch<DD, MM, true>(tm_x, tm_w, s_packed, d_bias, y, p, smem, grid, st)                   \
+                       : l1_launch<DD, MM, false>(tm_x, tm_w, s_packed, d_bias, y, p, smem, grid, st);
+    int rc = -1;
     CNA_L1_CASE(3, 8)
     CNA_L1_CASE(5, 8)
     CNA_L1_CASE(3, 4)
     CNA_L1_CASE(5, 4)
 #undef CNA_L1_CASE
-    CNA_FAIL("no kernel instance for this (d, M)");
+    if (rc < 0) CNA_FAIL("no kernel instance for this (d, M)");
+    if (rc == 0 && prof_on) {
+        long long h[32];
+        CNA_CUDA(cudaStreamSynchronize(st));
+        CNA_CUDA(cudaMemcpy(h, prof_dev, sizeof(h), cudaMemcpyDeviceToHost));
+        const int steps = ((p.ntiles + grid - 1) / grid) * p.nchunks;      // chunk-steps of CTA 0
+        fprintf(stderr, "[L1PROF d=%d N=%d sep=%d tiles/cta=%d chunks=%d nnt=%d sx=%d sw=%d] per chunk-step cycles: xprod wait %lld other %lld | wprod wait %lld other %lld | "
+                        "mma acc_empty %lld a_full %lld w_full %lld issue %lld | g0 xs_full %lld taps %lld a_empty %lld store %lld loop %lld | "
+                        "g1 xs_full %lld taps %lld a_empty %lld store %lld loop %lld | epi wait %lld drain %lld (per tile)\n",
+                d, N, separable, (p.ntiles + grid - 1) / grid, p.nchunks, p.nnt, p.sx, p.sw, h[1] / steps, h[0] / steps, h[2] / steps, h[20] / steps,
+                h[3] / steps, h[4] / steps, h[5] / steps, h[17] / steps, 2 * h[6] / steps, 2 * h[7] / steps, 2 * h[8] / steps, 2 * h[9] / steps,
+                2 * h[10] / steps, 2 * h[12] / steps, 2 * h[13] / steps, 2 * h[14] / steps, 2 * h[15] / steps, 2 * h[16] / steps,
+                h[18] / ((p.ntiles + grid - 1) / grid), h[19] / ((p.ntiles + grid - 1) / grid));
+    }
+    return rc;
 }
 
 }  // extern "C"

@@ -17,6 +17,8 @@ CASES = [
     (2, 24, 288, 3, 8, 6, 11, True),      # N = 288 = 2 x 144
     (2, 16, 32, 5, 4, 30, 17, True),      # M = 4, separable 5 + 5
     (1, 8, 16, 3, 8, 3, 3, False),        # tiny image: R = H = 3, mostly empty tile
+    (2, 24, 32, 3, 8, 90, 100, False),    # 180 one-row tiles on 148 SMs, 3 K-chunks: the two producer groups swap parity per tile
+    (2, 24, 32, 3, 8, 90, 100, True),
 ]
 
 

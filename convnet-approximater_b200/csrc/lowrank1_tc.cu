@@ -45,6 +45,8 @@ struct L1Params {
     int R, G, ntiles, nchunks;            // rows per tile, B*H, tiles, K-chunks of 64 wide channels
     int NT, nnt, nbuf, sw, sx;            // N-tile width, N-tiles, TMEM accumulator buffers, D ring depth, x ring depth
     int WP, RP, pad;                      // halo box: W + 2 pad columns, R + 2 pad rows
+    int hrun;                             // 1: row-run slot mapping
+    int WS;                               // slot pitch of a tile row: W (scattered mapping) or W rounded up to 4 (row runs)
     int debug;                            // CNA_L1_DEBUG ablations: 1 no taps, 2 no UMMAs, 8 no x loads, 16 no D loads
     long long* prof;                      // CNA_L1_PROF: per-role wait/work cycle counters of CTA 0 (debugging aid), else NULL
     uint32_t seg_box_bytes, seg_bytes, wblk_bytes, xs_stage;
@@ -124,7 +126,9 @@ struct L1Prof {
 };
 
 // D: basis filter size (d x d), M: bases per input channel (wide channel c*M+m), SEP: separable (d,1).(1,d) form
-template <int D, int M, bool SEP>
+//   HRUN: a thread's 4 pixels are 4 consecutive columns of one row (slot m = r*WS + w, WS = W rounded up to 4): the D+3 inputs of
+//   a row are loaded once and reused by all D taps and 4 outputs — 1.6x (5x5) fewer instructions than the scattered mapping
+template <int D, int M, bool SEP, bool HRUN>
 __global__ void __launch_bounds__(kL1Threads, 1)
 lowrank1_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                       const float* __restrict__ s_packed, const float* __restrict__ d_bias, __nv_bfloat16* __restrict__ y,
@@ -257,16 +261,32 @@ lowrank1_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         const int grp = (warp - 3) >> 3;
         const int pt = threadIdx.x - 96 - grp * kL1GroupThreads;
         const int u = pt & 7, pl = pt >> 3;
-        int rk[4];
+        int rk[4], wk[4];
         uint32_t xoff[4], aoff[4];
+        if constexpr (HRUN) {
+            // 32 runs per group = (row, 4-column run); a warp's four runs sit in four different rows (row pitch % 128 B != 0, 64 B:
+            // the x loads of a warp then fall into distinct banks)
+            const int CR = p.WS >> 2;
+            const int r_low = pl & 3, rest = pl >> 2;
+            const int r_high = rest / CR, cj = rest - r_high * CR;
+            const int rr = r_high * 4 + r_low;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int m = pl + 32 * k;
-            rk[k] = m / p.W;
-            const int wk = m - rk[k] * p.W;
-            // slots past the tile (rk >= R) compute on slot 0's data and are never stored
-            xoff[k] = rk[k] < p.R ? (uint32_t)((rk[k] * p.WP + wk) * CPC + (u * 8) / M) * 2u : (uint32_t)((u * 8) / M) * 2u;
-            aoff[k] = (uint32_t)m * 128u + (uint32_t)((u ^ (m & 7)) * 16);      // 128B swizzle: 16-byte unit u of row m lands at u ^ (m % 8)
+            for (int k = 0; k < 4; ++k) {
+                rk[k] = rr; wk[k] = 4 * cj + k;
+                const int m = rr * p.WS + wk[k];
+                xoff[k] = rr < p.R ? (uint32_t)((rr * p.WP + 4 * cj) * CPC + u) * 2u : (uint32_t)u * 2u;      // the run's first column
+                aoff[k] = (uint32_t)m * 128u + (uint32_t)((u ^ (m & 7)) * 16);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int m = pl + 32 * k;
+                rk[k] = m / p.W;
+                wk[k] = m - rk[k] * p.W;
+                // slots past the tile (rk >= R) compute on slot 0's data and are never stored
+                xoff[k] = rk[k] < p.R ? (uint32_t)((rk[k] * p.WP + wk[k]) * CPC + (u * 8) / M) * 2u : (uint32_t)((u * 8) / M) * 2u;
+                aoff[k] = (uint32_t)m * 128u + (uint32_t)((u ^ (m & 7)) * 16);      // 128B swizzle: 16-byte unit u of row m lands at u ^ (m % 8)
+            }
         }
         const uint32_t row_pitch = (uint32_t)p.WP * CPC * 2u;
         const uint32_t a_addr = base + p.off_a + grp * p.a_buf;
@@ -281,7 +301,7 @@ lowrank1_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             uint32_t xo[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                valid[k] = (rk[k] < p.R) && (g0 + rk[k] < p.G);
+                valid[k] = (rk[k] < p.R) && (wk[k] < p.W) && (g0 + rk[k] < p.G);
                 xo[k] = xoff[k] + ((rk[k] >= R1 && rk[k] < p.R) ? p.seg_bytes : 0u);
             }
             for (int ch = 0; ch < p.nchunks; ++ch, ++q) {
@@ -296,7 +316,83 @@ lowrank1_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 uint32_t xr[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) xr[k] = stage + xo[k];
-                if constexpr (!SEP) {
+                if constexpr (HRUN && !SEP) {
+                    float2 acc[4][4];
+                    float2 bs[4];
+                    l1_lds_f8<D * D * 256>(wb, bs);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) acc[k][e] = bs[e];
+                    if (!(p.debug & 1)) {
+                        uint32_t xrow = xr[0];
+                        l1_static_for<0, D>([&](auto ic) {
+                            constexpr int i = decltype(ic)::value;
+                            float2 X[D + 3];                                  // the row's inputs, each feeding up to D taps x 4 outputs
+                            l1_static_for<0, D + 3>([&](auto cc) {
+                                constexpr int c = decltype(cc)::value;
+                                const float v = l1_lds_bf16<c * (CPC * 2)>(xrow);
+                                X[c] = make_float2(v, v);
+                            });
+                            l1_static_for<0, D>([&](auto jc) {
+                                constexpr int j = decltype(jc)::value;
+                                float2 w[4];
+                                l1_lds_f8<(i * D + j) * 256>(wb, w);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) acc[k][e] = l1_ffma2(X[k + j], w[e], acc[k][e]);
+                            });
+                            xrow += row_pitch;
+                        });
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) pk[k][e] = l1_pack(acc[k][e]);
+                } else if constexpr (HRUN && SEP) {
+                    float2 acc[4][4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) acc[k][e] = make_float2(0.f, 0.f);
+                    if (!(p.debug & 1)) {
+                        uint32_t xrow[D];
+#pragma unroll
+                        for (int i = 0; i < D; ++i) xrow[i] = xr[0] + i * row_pitch;
+                        // column by column: the bf16-rounded vertical pass of column c feeds the outputs k = c - j
+                        l1_static_for<0, D + 3>([&](auto cc) {
+                            constexpr int c = decltype(cc)::value;
+                            float2 tc[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) tc[e] = make_float2(0.f, 0.f);
+                            l1_static_for<0, D>([&](auto ic) {
+                                constexpr int i = decltype(ic)::value;
+                                const float v = l1_lds_bf16<c * (CPC * 2)>(xrow[i]);
+                                float2 w[4];
+                                l1_lds_f8<i * 256>(wb, w);                        // v taps: rows 0 .. D-1
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) tc[e] = l1_ffma2(make_float2(v, v), w[e], tc[e]);
+                            });
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) tc[e] = l1_round_bf16(tc[e]);
+                            l1_static_for<0, 4>([&](auto kc) {
+                                constexpr int k = decltype(kc)::value;
+                                constexpr int j = c - k;
+                                if constexpr (j >= 0 && j < D) {
+                                    float2 wh[4];
+                                    l1_lds_f8<(D + j) * 256>(wb, wh);             // h taps: rows D .. 2D-1
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) acc[k][e] = l1_ffma2(tc[e], wh[e], acc[k][e]);
+                                }
+                            });
+                        });
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) pk[k][e] = l1_pack(acc[k][e]);
+                } else                 if constexpr (!SEP) {
                     float2 acc[4][4];
                     float2 bs[4];
                     l1_lds_f8<D * D * 256>(wb, bs);
@@ -402,13 +498,13 @@ lowrank1_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         const int lg = warp & 3;
         const uint32_t lane_addr = (uint32_t)(lg * 32) << 16;
         const int m = lg * 32 + lane;
-        const int r = m / p.W, w = m - r * p.W;
+        const int r = m / p.WS, w = m - r * p.WS;
         L1Prof pf(p.prof, m == 0);
         for (int it = 0; it < my_tiles; ++it) {
             const int buf = it % p.nbuf;
             const uint32_t use = (uint32_t)(it / p.nbuf);
             const int g0 = (first + it * step) * p.R;
-            const bool ok = (r < p.R) && (g0 + r < p.G);
+            const bool ok = (r < p.R) && (w < p.W) && (g0 + r < p.G);
             __nv_bfloat16* yrow = y + ((long long)(g0 + r) * p.W + w) * p.N;
             pf.lap(19);
             mbar_wait(bar(L1_ACC_FULL + buf), use & 1u);
@@ -489,6 +585,18 @@ static size_t l1_plan(L1Params& p, int B, int H, int W, int C, int N, int M, int
     p.B = B; p.H = H; p.W = W; p.C = C; p.N = N;
     p.pad = d / 2;
     p.R = std::min(128 / W, H);
+    p.WS = W;
+    p.hrun = 0;
+    {   // row-run mapping: rows of WS = W rounded up to 4 slots, R a multiple of 4 (a warp's four runs sit in four rows)
+        const int ws = (W + 3) / 4 * 4;
+        const int rh = ws <= 32 ? (128 / ws) / 4 * 4 : 0;
+        static const int force = [] { const char* e = getenv("CNA_L1_MAP"); return e ? atoi(e) : -1; }();
+        const bool fits = M == 8 && rh >= 4 && rh <= H;
+        // fewer instructions per pixel, but padded rows waste MMA rows: take it when the producers are the bound (separable form,
+        // 5x5 filters) or when the padding costs < 5 % of the tile
+        const bool wins = separable || d >= 5 || rh * W * 100 >= p.R * W * 95;
+        if (fits && (force < 0 ? wins : force == 1)) { p.hrun = 1; p.R = rh; p.WS = ws; }
+    }
     p.G = B * H;
     p.ntiles = (p.G + p.R - 1) / p.R;
     p.nchunks = C / cpc;
@@ -524,15 +632,15 @@ static size_t l1_plan(L1Params& p, int B, int H, int W, int C, int N, int M, int
     return (size_t)p.off_bar + 1024 + 1024;
 }
 
-template <int D, int M, bool SEP>
+template <int D, int M, bool SEP, bool HRUN>
 static int l1_launch(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const float* s_packed, const float* d_bias, void* y,
                      const L1Params& p, size_t smem, int grid, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        CNA_CUDA(cudaFuncSetAttribute(lowrank1_fused_kernel<D, M, SEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CNA_CUDA(cudaFuncSetAttribute(lowrank1_fused_kernel<D, M, SEP, HRUN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
-    lowrank1_fused_kernel<D, M, SEP><<<grid, kL1Threads, smem, st>>>(tm_x, tm_w, s_packed, d_bias, (__nv_bfloat16*)y, p);
+    lowrank1_fused_kernel<D, M, SEP, HRUN><<<grid, kL1Threads, smem, st>>>(tm_x, tm_w, s_packed, d_bias, (__nv_bfloat16*)y, p);
     CNA_LAUNCH_OK();
     return 0;
 }
@@ -587,25 +695,31 @@ int cna_lowrank1_fused_forward(const void* x, const float* s_packed, const void*
         p.prof = prof_dev;
     }
 #define CNA_L1_CASE(DD, MM)                                                                                            \
-    if (d == DD && M == MM)                                                                                            \
-        rc = separable ? l1_launch<DD, MM, true>(tm_x, tm_w, s_packed, d_bias, y, p, smem, grid, st)                   \
-                       : l1_launch<DD, MM, false>(tm_x, tm_w, s_packed, d_bias, y, p, smem, grid, st);
+    if (d == DD && M == MM && !p.hrun)                                                                                 \
+        rc = separable ? l1_launch<DD, MM, true, false>(tm_x, tm_w, s_packed, d_bias, y, p, smem, grid, st)            \
+                       : l1_launch<DD, MM, false, false>(tm_x, tm_w, s_packed, d_bias, y, p, smem, grid, st);
     int rc = -1;
     CNA_L1_CASE(3, 8)
     CNA_L1_CASE(5, 8)
     CNA_L1_CASE(3, 4)
     CNA_L1_CASE(5, 4)
 #undef CNA_L1_CASE
+    if (p.hrun && M == 8 && d == 3)
+        rc = separable ? l1_launch<3, 8, true, true>(tm_x, tm_w, s_packed, d_bias, y, p, smem, grid, st)
+                       : l1_launch<3, 8, false, true>(tm_x, tm_w, s_packed, d_bias, y, p, smem, grid, st);
+    if (p.hrun && M == 8 && d == 5)
+        rc = separable ? l1_launch<5, 8, true, true>(tm_x, tm_w, s_packed, d_bias, y, p, smem, grid, st)
+                       : l1_launch<5, 8, false, true>(tm_x, tm_w, s_packed, d_bias, y, p, smem, grid, st);
     if (rc < 0) CNA_FAIL("no kernel instance for this (d, M)");
     if (rc == 0 && prof_on) {
         long long h[32];
         CNA_CUDA(cudaStreamSynchronize(st));
         CNA_CUDA(cudaMemcpy(h, prof_dev, sizeof(h), cudaMemcpyDeviceToHost));
         const int steps = ((p.ntiles + grid - 1) / grid) * p.nchunks;      // chunk-steps of CTA 0
-        fprintf(stderr, "[L1PROF d=%d N=%d sep=%d tiles/cta=%d chunks=%d nnt=%d sx=%d sw=%d] per chunk-step cycles: xprod wait %lld other %lld | wprod wait %lld other %lld | "
+        fprintf(stderr, "[L1PROF d=%d N=%d sep=%d hrun=%d tiles/cta=%d chunks=%d nnt=%d sx=%d sw=%d] per chunk-step cycles: xprod wait %lld other %lld | wprod wait %lld other %lld | "
                         "mma acc_empty %lld a_full %lld w_full %lld issue %lld | g0 xs_full %lld taps %lld a_empty %lld store %lld loop %lld | "
                         "g1 xs_full %lld taps %lld a_empty %lld store %lld loop %lld | epi wait %lld drain %lld (per tile)\n",
-                d, N, separable, (p.ntiles + grid - 1) / grid, p.nchunks, p.nnt, p.sx, p.sw, h[1] / steps, h[0] / steps, h[2] / steps, h[20] / steps,
+                d, N, separable, p.hrun, (p.ntiles + grid - 1) / grid, p.nchunks, p.nnt, p.sx, p.sw, h[1] / steps, h[0] / steps, h[2] / steps, h[20] / steps,
                 h[3] / steps, h[4] / steps, h[5] / steps, h[17] / steps, 2 * h[6] / steps, 2 * h[7] / steps, 2 * h[8] / steps, 2 * h[9] / steps,
                 2 * h[10] / steps, 2 * h[12] / steps, 2 * h[13] / steps, 2 * h[14] / steps, 2 * h[15] / steps, 2 * h[16] / steps,
                 h[18] / ((p.ntiles + grid - 1) / grid), h[19] / ((p.ntiles + grid - 1) / grid));

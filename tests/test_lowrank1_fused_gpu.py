@@ -19,6 +19,8 @@ CASES = [
     (1, 8, 16, 3, 8, 3, 3, False),        # tiny image: R = H = 3, mostly empty tile
     (2, 24, 32, 3, 8, 90, 100, False),    # 180 one-row tiles on 148 SMs, 3 K-chunks: the two producer groups swap parity per tile
     (2, 24, 32, 3, 8, 90, 100, True),
+    (2, 16, 64, 3, 8, 20, 16, False),     # W % 4 == 0: row-run mapping at no padding cost (3x3, d x d form)
+    (3, 8, 32, 5, 8, 9, 30, True),        # row runs, separable 5 + 5, 4-row tiles straddling the 9-row images
 ]
 
 

@@ -120,3 +120,30 @@ def test_product_package_never_imports_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 assert not pat.search(open(os.path.join(dp, f)).read()), (dp, f)
+
+
+def test_lowrank1_pack_layout_cpu():
+    """Host-side packing of the scheme-1 basis filters (pure tensor re-layout, no kernel): per 64 wide channels
+    [rows][64] with unit u's channels 8u..8u+3 at floats [4u,4u+4) and 8u+4..8u+7 at [32+4u, 32+4u+4)."""
+    import torch
+    from approx import backend as B
+    from approx.layers import LowRankExpConvV1
+    torch.manual_seed(0)
+    C, M, d = 16, 8, 3
+    layer = LowRankExpConvV1(C, 32, d, 1, 1, num_base=M)
+    sp = B.lowrank1_pack_s(layer.s_conv, M)
+    assert sp.shape == (C * M // 64, d * d + 1, 64) and sp.dtype == torch.float32
+    w = layer.s_conv.weight.detach().to(torch.bfloat16).float().reshape(C * M, d * d)
+    for cm in (0, 5, 63, 64, 77, 127):
+        chunk, local = divmod(cm, 64)
+        u, e = divmod(local, 8)
+        pos = (e // 4) * 32 + u * 4 + (e % 4)
+        assert torch.equal(sp[chunk, :d * d, pos], w[cm])
+        assert sp[chunk, d * d, pos] == layer.s_conv.bias.detach()[cm]
+    layer.s_conv = __import__("approx.layers.low_rank_conv", fromlist=["SeparableConv"]).SeparableConv(C, M, (d, d), (1, 1), (1, 1))
+    sp = B.lowrank1_pack_s(layer.s_conv, M)
+    assert sp.shape == (C * M // 64, 2 * d, 64)
+    v = layer.s_conv.v_conv.weight.detach().to(torch.bfloat16).float().reshape(C * M, d)
+    h = layer.s_conv.h_conv.weight.detach().to(torch.bfloat16).float().reshape(C * M, d)
+    cm = 70; u, e = divmod(cm - 64, 8); pos = (e // 4) * 32 + u * 4 + (e % 4)
+    assert torch.equal(sp[1, :d, pos], v[cm]) and torch.equal(sp[1, d:, pos], h[cm])

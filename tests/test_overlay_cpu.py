@@ -66,3 +66,76 @@ def test_reference_models_and_configs_drive_this_backend():
     out = subprocess.run([sys.executable, "-c", SCRIPT, pkg], env=env, capture_output=True, text=True, cwd="/tmp", timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "overlay ok" in out.stdout
+
+
+REF_SCRIPT = r"""
+import sys, types
+for name in ("timm", "timm.data", "timm.models", "timm.utils", "timm.loss", "timm.optim", "timm.scheduler", "ptflops", "cvxpy"):
+    sys.modules.setdefault(name, types.ModuleType(name))
+import torch
+import approx.layers, approx.core
+from approx.models import build_model
+from approx.core import build_app
+from approx.filters import build_filter
+from approx.utils import init_cfg, get_cfg
+mode, cfg_file, ckpt_in, ckpt_out = sys.argv[1:5]
+init_cfg(cfg_file)
+cfg = get_cfg()
+torch.manual_seed(0)
+model = build_model(dict(cfg.model, init_cfg=None))
+app = build_app(cfg.app, deploy=False)
+filters = [build_filter(f) for f in (cfg.filters or [])]
+model.register_switchable(app.src_type, filters)
+for idx in range(model.length_switchable):
+    model.set_switchable_module(idx, app.initialize, src=model.get_switchable_module(idx))
+post = type(app).__name__ != "LowRankExpV1"     # LowRankExpV1.optimize needs cvxpy even for its SVD branch; decomp() here needs the GPU
+if mode == "reference":
+    assert approx.layers.__file__.startswith("/root/reference"), approx.layers.__file__
+    for sub in model.switchable_modules():
+        if post:
+            app.optimize(sub)                   # the reference's own CPU fit (torch.linalg.svd)
+else:
+    assert not approx.layers.__file__.startswith("/root/reference"), approx.layers.__file__
+if ckpt_in != "-":
+    sd = torch.load(ckpt_in, map_location="cpu")["state_dict"]
+    missing, unexpected = model.load_state_dict(sd, strict=True)     # same keys, same shapes, both directions
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+torch.save(dict(state_dict=model.state_dict()), ckpt_out)       # before post-processing: what the other side loads
+for idx in range(model.length_switchable if post else 0):       # Runner.run's post-process step (Substitution -> replacement layer)
+    model.set_switchable_module(idx, app.postprocess, sub=model.get_switchable_module(idx))
+torch.save(dict(state_dict=model.state_dict()), ckpt_out + ".post")
+print("ckpt ok", len(model.state_dict()))
+"""
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present on this machine")
+@pytest.mark.parametrize("cfg", ["configs/msca-rep/msca-rep_d1_fix_mscan-t.py",
+                                 "configs/low-rank-exp/low-rank-exp-v1_l2345_svd_dodecomp_alexnet.py"])
+def test_checkpoints_interchange_with_the_reference(cfg, tmp_path):
+    """A checkpoint written by the unmodified reference (its layers, its CPU fit) loads strictly into the same model built on
+    this backend's layers, and the post-processed checkpoints of both carry identical keys, shapes and values."""
+    import torch
+    pkg = os.path.join(ROOT, "convnet-approximater_b200")
+    cfg_file = os.path.join("/root/reference", cfg)
+    ref_ckpt, our_ckpt = str(tmp_path / "ref.pth"), str(tmp_path / "ours.pth")
+
+    def run(mode, ckpt_in, ckpt_out):
+        if mode == "reference":
+            env = dict(os.environ, PYTHONPATH=REF)
+            env.pop("CNA_REFERENCE_SRC", None)
+        else:
+            env = dict(os.environ, CNA_REFERENCE_SRC=REF, PYTHONPATH=pkg)
+        script = REF_SCRIPT
+        out = subprocess.run([sys.executable, "-c", script, mode, cfg_file, ckpt_in, ckpt_out], env=env, capture_output=True,
+                             text=True, cwd="/tmp", timeout=600)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+        assert "ckpt ok" in out.stdout
+
+    run("reference", "-", ref_ckpt)
+    run("overlay", ref_ckpt, our_ckpt)
+    a = torch.load(ref_ckpt + ".post", map_location="cpu")["state_dict"]
+    b = torch.load(our_ckpt + ".post", map_location="cpu")["state_dict"]
+    assert list(a) == list(b)
+    for k in a:
+        assert a[k].shape == b[k].shape and torch.equal(a[k], b[k]), k

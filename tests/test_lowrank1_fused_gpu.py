@@ -92,3 +92,34 @@ def test_full_size_agrees_with_unfused_path():
     assert torch.isfinite(y.float()).all()
     num = (y.float() - y2.float()).norm() / y2.float().norm()
     assert num < 1e-3, float(num)
+
+
+def test_random_shapes_agree_with_unfused_path():
+    """Seeded sweep over ragged shapes (both slot mappings, both forms, 1-3 tiles per SM, 1..6 K-chunks): the tcgen05 kernel
+    against the FFMA kernels on the same bf16 inputs."""
+    import random
+    from approx import backend as B
+    rng = random.Random(1234)
+    done = 0
+    while done < 16:
+        M = rng.choice([4, 8])
+        d = rng.choice([3, 5])
+        C = (64 // M) * rng.randint(1, 6)
+        if C % 8:
+            continue
+        N = 16 * rng.randint(1, 24)
+        if N > 256 and N % 32:
+            continue
+        H, W = rng.randint(d, 40), rng.randint(d, 60)
+        Bn = rng.randint(1, 5)
+        sep = rng.random() < 0.5
+        if not B.lowrank1_fused_supported(Bn, H, W, C, N, M, d, sep):
+            continue
+        m = build(C, N, d, M, sep, 100 + done).cuda().eval()
+        x = torch.randn(Bn, H, W, C, device="cuda", generator=torch.Generator(device="cuda").manual_seed(done)).bfloat16()
+        with torch.no_grad():
+            y = m.forward_nhwc(x)
+            y2 = m.forward_nhwc(x, fused=False)
+        err = float((y.float() - y2.float()).norm() / y2.float().norm())
+        assert err < 1e-3, (Bn, C, N, d, M, H, W, sep, err)
+        done += 1

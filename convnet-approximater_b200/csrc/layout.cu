@@ -2,6 +2,10 @@
 // every kernel in this library works on NHWC).  Tiled 32x32 shared-memory transposes.
 #include "common.cuh"
 
+#include <algorithm>
+#include <cstdint>
+#include <type_traits>
+
 namespace cna {
 
 // src [B][C][HW] -> dst [B][HW][c_pad]
@@ -24,6 +28,25 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const TI* __restrict_
     for (int i = 0; i < 4; ++i) {
         int p = p0 + ty + i * 8, c = c0 + tx;
         if (p < HW && c < c_pad) d[(size_t)p * c_pad + c] = from_f32<TO>(tile[tx][ty + i * 8]);
+    }
+}
+
+// Few-channel images (C <= 8: the network input) -> bf16 NHWC zero-padded to CPAD channels: a thread owns one pixel, reads its C
+// planes (coalesced across the warp) and writes CPAD * 2 bytes with 16-byte stores.  The 32 x 32 tile transpose above leaves
+// 29 of 32 tile rows empty for C = 3 and issues 2-byte stores; this is the e2e path's first kernel (bench.py, approx/pipeline.py).
+template <typename TI, int CPAD>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_smallc_kernel(const TI* __restrict__ src, __nv_bfloat16* __restrict__ dst, int C,
+                                                                  int HW, long long total) {
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long b = idx / HW;
+        const int p = (int)(idx - b * HW);
+        const TI* s = src + (size_t)b * C * HW + p;
+        __nv_bfloat16 v[CPAD];
+#pragma unroll
+        for (int c = 0; c < CPAD; ++c) v[c] = c < C ? from_f32<__nv_bfloat16>(to_f32(ldg(s + (size_t)c * HW))) : __float2bfloat16_rn(0.f);
+        uint4* d = reinterpret_cast<uint4*>(dst + (size_t)idx * CPAD);
+#pragma unroll
+        for (int q = 0; q < CPAD / 8; ++q) d[q] = *reinterpret_cast<const uint4*>(&v[q * 8]);
     }
 }
 
@@ -97,6 +120,16 @@ __global__ void __launch_bounds__(256) maxpool2x2_bf16x8_kernel(const uint4* __r
 
 template <typename TI, typename TO>
 static int launch_to_nhwc(const void* src, void* dst, int B, int C, int H, int W, int c_pad, cudaStream_t st) {
+    if constexpr (std::is_same<TO, __nv_bfloat16>::value) {
+        if (C <= 8 && (c_pad == 8 || c_pad == 16) && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            const long long total = (long long)B * H * W;
+            const int grid = (int)std::min<long long>(ceil_div_ll(total, 256), 148LL * 16);
+            if (c_pad == 8) nchw_to_nhwc_smallc_kernel<TI, 8><<<grid, 256, 0, st>>>((const TI*)src, (__nv_bfloat16*)dst, C, H * W, total);
+            else nchw_to_nhwc_smallc_kernel<TI, 16><<<grid, 256, 0, st>>>((const TI*)src, (__nv_bfloat16*)dst, C, H * W, total);
+            CNA_LAUNCH_OK();
+            return 0;
+        }
+    }
     dim3 grid(ceil_div(H * W, 32), ceil_div(c_pad, 32), B);
     nchw_to_nhwc_kernel<TI, TO><<<grid, 256, 0, st>>>((const TI*)src, (TO*)dst, C, H * W, c_pad);
     CNA_LAUNCH_OK();

@@ -46,6 +46,18 @@ def test_layout_roundtrip(B, dt, shape, c_pad):
     assert B.to_nhwc(xcl).data_ptr() == xcl.data_ptr()
 
 
+@pytest.mark.parametrize("shape,c_pad", [((4, 3, 224, 224), 16), ((2, 8, 9, 11), 8), ((3, 1, 17, 5), 16), ((2, 5, 6, 6), 8)])
+@pytest.mark.parametrize("src_dt", [torch.float32, torch.bfloat16])
+def test_image_layout_kernel(B, shape, c_pad, src_dt):
+    """Few-channel NCHW images -> zero-padded bf16 NHWC (the first kernel of the host-buffer pipeline): exact re-layout."""
+    torch.manual_seed(1)
+    x = torch.randn(*shape).to(src_dt)
+    xn = B.to_nhwc(x.cuda(), c_pad, dtype=torch.bfloat16)
+    ref = torch.zeros(shape[0], shape[2], shape[3], c_pad, dtype=torch.bfloat16)
+    ref[..., :shape[1]] = x.permute(0, 2, 3, 1).to(torch.bfloat16)
+    assert xn.dtype == torch.bfloat16 and torch.equal(xn.cpu(), ref)
+
+
 CONV_CASES = [
     # B, C, H, W, N, taps, axis, sh, sw, pad
     (2, 16, 12, 10, 8, 3, 0, 1, 1, 1),

@@ -9,6 +9,8 @@ from __future__ import annotations
 
 import torch
 
+from approx import backend as B
+
 
 class HostPipeline:
     def __init__(self, module, device, depth: int = 2):
@@ -35,6 +37,11 @@ class HostPipeline:
         with torch.cuda.stream(self.s_run):
             self.s_run.wait_event(self.ev_in_ready[i])
             y = self.module(self.xbuf[i])
+            if (y.dim() == 4 and y_host.is_contiguous() and not y.is_contiguous() and y.permute(0, 2, 3, 1).is_contiguous()
+                    and y.dtype == y_host.dtype):
+                # the module hands back a channels_last view; an NCHW-contiguous host buffer needs the transpose: the library's
+                # tile-transpose kernel here, instead of the strided element copy torch would insert before the D2H
+                y = B.to_nchw_contiguous(y.permute(0, 2, 3, 1))
             self.ev_in_free[i].record(self.s_run)
             self.ev_out_ready[i].record(self.s_run)
         with torch.cuda.stream(self.s_out):

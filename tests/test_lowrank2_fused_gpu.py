@@ -161,3 +161,24 @@ def test_tapconv3_tcgen05(case, axis):
     wv, _ = B.lowrank2_pack(w.cuda().float(), torch.zeros(64, K, 1, 3, device="cuda"))
     out = B.tapconv3_tc(B.to_nhwc(x.cuda()).contiguous(), wv, axis)
     assert O.compare4d(ref.float(), out[..., :K].permute(0, 3, 1, 2).float().cpu()) < 1e-3
+
+
+@pytest.mark.parametrize("channels_last_out", [False, True])
+def test_host_pipeline_matches_direct_call(channels_last_out):
+    """approx.pipeline.HostPipeline (pinned host buffers, 3 streams, ring of device inputs): every queued batch comes back
+    bit-identical to `module(x.cuda())`, for an NCHW-contiguous and for a channels_last host output buffer."""
+    from approx.layers import LowRankExpConvV2
+    from approx.pipeline import HostPipeline
+    torch.manual_seed(3)
+    m = LowRankExpConvV2(3, 16, (3, 3), (1, 1), (1, 1), out_channels=64).cuda().bfloat16().eval()
+    xs = [torch.randn(4, 3, 40, 36).bfloat16().pin_memory() for _ in range(5)]
+    fmt = torch.channels_last if channels_last_out else torch.contiguous_format
+    ys = [torch.empty(4, 64, 40, 36, dtype=torch.bfloat16).contiguous(memory_format=fmt).pin_memory() for _ in xs]
+    pipe = HostPipeline(m, "cuda:0", depth=2)
+    for x, y in zip(xs, ys):
+        pipe.submit(x, y)
+    pipe.wait()
+    with torch.no_grad():
+        for x, y in zip(xs, ys):
+            ref = m(x.cuda()).cpu()
+            assert torch.equal(ref, y)

@@ -42,6 +42,7 @@ struct P {
     int ldtm;      // 1: 4 other warps run tcgen05.ld loops concurrently
     int rot;       // >1: rotate the accumulator per INSTRUCTION over `rot` independent 64-column accumulators (N=64 only)
     long long* out;
+    int M = 128;   // UMMA M (128, or 64: half the A rows — the transposed-GEMM option of DESIGN.md §7)
 };
 
 // one CTA, 9 warps: warp 0 issues MMAs, warps 1-4 optional smem-store noise, warps 5-8 optional TMEM-load noise
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(288, 1) umma_rate(P p) {
     tc_fence_after_sync();
     const uint32_t tmem = tmem_slot;
     if (warp == 0) {
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | (8u << 24);
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(p.M >> 4) << 24);
         const uint64_t bdesc = desc_hi(16, 8 * 128, 2) + ((base + 48 * 1024) >> 4);      // B: 128B swizzle, up to 3 x 256 rows? keep 1 tap = N rows
         uint64_t adesc; uint32_t tap_step, kk_step;
         if (p.mode == 0) { adesc = desc_hi(16, 8 * 128, 2) + (base >> 4); tap_step = 16 * 128; kk_step = 32; }
@@ -93,7 +94,21 @@ __global__ void __launch_bounds__(288, 1) umma_rate(P p) {
         t1 = clock64();
         if (lane == 0) { p.out[0] = t1 - t0; stop_flag = 1; }
     } else if (warp <= 4) {
-        if (p.sts_kb > 0) {
+        if (p.sts_kb < 0) {
+            // shared-memory LOAD noise (what CUDA-core producer warps next to the MMA issuer generate)
+            const uint32_t nb = base + 96 * 1024 + (warp - 1) * 8192 + lane * 16;
+            long long n = 0; uint32_t sink = 0;
+            while (!stop_flag) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    uint32_t a, b, c, d;
+                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(nb + i * 512));
+                    sink ^= a ^ b ^ c ^ d;
+                }
+                ++n;
+            }
+            if (lane == 0) p.out[1 + warp] = n * 8 + (sink == 0x12345 ? 1 : 0);
+        } else if (p.sts_kb > 0) {
             // each warp instruction stores 512 B; noise region at base + 96 KB (32 KB)
             const uint32_t nb = base + 96 * 1024 + (warp - 1) * 8192 + lane * 16;
             long long n = 0;
@@ -392,6 +407,26 @@ int main() {
                 if (noise == 2) { double n = out[6] + out[7] + out[8] + out[9]; printf("  LDTM %.1f B/cyc", n * 32 * 64 * 4 / out[0]); }
                 printf("\n");
             }
+    printf("== shared-memory LOAD flood from 4 other warps (ld.shared.v4) ==\n");
+    for (int mode = 0; mode < 3; ++mode)
+        for (int ni = 0; ni < 3; ++ni) {
+            P p{mode, Ns[ni], 400, -1, 0, 1, out};
+            for (int i = 0; i < 16; ++i) out[i] = 0;
+            umma_rate<<<1, 288, 200 * 1024>>>(p);
+            CK(cudaDeviceSynchronize());
+            double kb = out[2] + out[3] + out[4] + out[5];
+            printf("%-32s N=%3d +LDS flood   : %7.1f cyc/UMMA  LDS %.1f B/cyc\n", mname[mode], p.N, (double)out[0] / (p.groups * 12.0), kb * 1024.0 / out[0]);
+        }
+    printf("== M = 64 (weights as the A operand of a transposed GEMM: 64 ranks x 16, pixels along N) ==\n");
+    for (int mode = 0; mode < 4; mode += 3)
+        for (int ni = 0; ni < 3; ++ni) {
+            P p{mode, Ns[ni], 400, 0, 0, 1, out, 64};
+            for (int i = 0; i < 16; ++i) out[i] = 0;
+            umma_rate<<<1, 288, 200 * 1024>>>(p);
+            CK(cudaDeviceSynchronize());
+            double per = (double)out[0] / (p.groups * 12.0);
+            printf("%-32s M= 64 N=%3d : %7.1f cyc/UMMA (%5.1f%% of tensor peak on its 64 x N x 16 MACs)\n", mname[mode], p.N, per, 100.0 * (64.0 * p.N / 256.0) / per);
+        }
     printf("== independent accumulators rotated per instruction (N=64) ==\n");
     for (int mode = 0; mode < 4; mode += 3)
         for (int rot = 1; rot <= 4; rot *= 2) {

@@ -160,6 +160,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 }
                 if (!ok) continue;
                 const int nvalid = min(32, p.N - n0);
+                uint4 pend = make_uint4(0, 0, 0, 0);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     if (q * 8 >= nvalid) break;
@@ -181,7 +182,9 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                     __nv_bfloat162 t2 = __floats2bfloat162_rn(f[4], f[5]), t3 = __floats2bfloat162_rn(f[6], f[7]);
                     o.x = *reinterpret_cast<uint32_t*>(&t0); o.y = *reinterpret_cast<uint32_t*>(&t1);
                     o.z = *reinterpret_cast<uint32_t*>(&t2); o.w = *reinterpret_cast<uint32_t*>(&t3);
-                    *(reinterpret_cast<uint4*>(yrow + n0) + q) = o;
+                    // 16 columns = one 32-byte store (N % 16 == 0 keeps every row 32-byte aligned)
+                    if (q & 1) st_global_v8(yrow + n0 + (q - 1) * 8, pend, o);
+                    else pend = o;
                 }
             }
         }

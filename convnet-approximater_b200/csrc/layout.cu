@@ -1,6 +1,7 @@
 // NCHW <-> NHWC boundary conversions (the reference's tensors are logical NCHW;
 // every kernel in this library works on NHWC).  Tiled 32x32 shared-memory transposes.
 #include "common.cuh"
+#include "ptx.cuh"
 
 #include <algorithm>
 #include <cstdint>
@@ -41,12 +42,16 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_smallc_kernel(const TI* __re
         const long long b = idx / HW;
         const int p = (int)(idx - b * HW);
         const TI* s = src + (size_t)b * C * HW + p;
-        __nv_bfloat16 v[CPAD];
+        alignas(16) __nv_bfloat16 v[CPAD];
 #pragma unroll
         for (int c = 0; c < CPAD; ++c) v[c] = c < C ? from_f32<__nv_bfloat16>(to_f32(ldg(s + (size_t)c * HW))) : __float2bfloat16_rn(0.f);
-        uint4* d = reinterpret_cast<uint4*>(dst + (size_t)idx * CPAD);
-#pragma unroll
-        for (int q = 0; q < CPAD / 8; ++q) d[q] = *reinterpret_cast<const uint4*>(&v[q * 8]);
+        __nv_bfloat16* d = dst + (size_t)idx * CPAD;
+        if constexpr (CPAD == 16) {
+            if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) ptx::st_global_v8(d, *reinterpret_cast<const uint4*>(&v[0]), *reinterpret_cast<const uint4*>(&v[8]));
+            else { reinterpret_cast<uint4*>(d)[0] = *reinterpret_cast<const uint4*>(&v[0]); reinterpret_cast<uint4*>(d)[1] = *reinterpret_cast<const uint4*>(&v[8]); }
+        } else {
+            reinterpret_cast<uint4*>(d)[0] = *reinterpret_cast<const uint4*>(&v[0]);
+        }
     }
 }
 

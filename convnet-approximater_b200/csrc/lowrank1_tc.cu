@@ -527,14 +527,18 @@ lowrank1_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 if (!ok) continue;
                 const int nvalid = min(32, p.N - n0);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (q * 8 >= nvalid) break;
-                    uint4 o;
-                    o.x = l1_pack(make_float2(__uint_as_float(v[q * 8 + 0]) + sbias[n0 + q * 8 + 0], __uint_as_float(v[q * 8 + 1]) + sbias[n0 + q * 8 + 1]));
-                    o.y = l1_pack(make_float2(__uint_as_float(v[q * 8 + 2]) + sbias[n0 + q * 8 + 2], __uint_as_float(v[q * 8 + 3]) + sbias[n0 + q * 8 + 3]));
-                    o.z = l1_pack(make_float2(__uint_as_float(v[q * 8 + 4]) + sbias[n0 + q * 8 + 4], __uint_as_float(v[q * 8 + 5]) + sbias[n0 + q * 8 + 5]));
-                    o.w = l1_pack(make_float2(__uint_as_float(v[q * 8 + 6]) + sbias[n0 + q * 8 + 6], __uint_as_float(v[q * 8 + 7]) + sbias[n0 + q * 8 + 7]));
-                    *(reinterpret_cast<uint4*>(yrow + n0) + q) = o;
+                for (int h = 0; h < 2; ++h) {                  // 16 columns = 32 bytes per store (rows are 32-byte aligned: N % 16 == 0)
+                    if (h * 16 >= nvalid) break;
+                    uint4 o[2];
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        const int c = h * 16 + t * 8;
+                        o[t].x = l1_pack(make_float2(__uint_as_float(v[c + 0]) + sbias[n0 + c + 0], __uint_as_float(v[c + 1]) + sbias[n0 + c + 1]));
+                        o[t].y = l1_pack(make_float2(__uint_as_float(v[c + 2]) + sbias[n0 + c + 2], __uint_as_float(v[c + 3]) + sbias[n0 + c + 3]));
+                        o[t].z = l1_pack(make_float2(__uint_as_float(v[c + 4]) + sbias[n0 + c + 4], __uint_as_float(v[c + 5]) + sbias[n0 + c + 5]));
+                        o[t].w = l1_pack(make_float2(__uint_as_float(v[c + 6]) + sbias[n0 + c + 6], __uint_as_float(v[c + 7]) + sbias[n0 + c + 7]));
+                    }
+                    st_global_v8(yrow + n0 + h * 16, o[0], o[1]);
                 }
             }
         }

@@ -60,6 +60,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+// 32-byte global store (STG.E.256 on sm_100a): one write transaction per full sector where a thread owns 32 contiguous bytes
+__device__ __forceinline__ void st_global_v8(void* ptr, uint4 lo, uint4 hi) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w),
+                 "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+                 : "memory");
+}
+
 // ---- fences ----------------------------------------------------------------------------------
 // generic-proxy smem writes -> visible to the async proxy (TMA store / UMMA operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {

@@ -59,7 +59,7 @@ h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
 print("max", nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM), flush=True)
 while True:
     print(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetPowerUsage(h) / 1000.0,
-          nv.nvmlDeviceGetCurrentClocksEventReasons(h), flush=True)
+          nv.nvmlDeviceGetCurrentClocksEventReasons(h), time.time(), flush=True)
     time.sleep(0.002)
 """
 
@@ -92,17 +92,16 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             f = line.split()
-            if len(f) == 3:
+            if len(f) == 4:
                 try:
-                    self.rows.append((int(f[0]), float(f[1]), int(f[2])))
+                    self.rows.append((int(f[0]), float(f[1]), int(f[2]), float(f[3])))
                 except ValueError:
                     pass
 
-    def mark(self):
-        """Number of samples so far (call at the start of the timed region)."""
-        return len(self.rows)
-
-    def stop(self, first=0):
+    def stop(self, t_load, t_beg, t_end):
+        """Samples stamped inside the timed region [t_beg, t_end] (host wall clock, both sides synchronised).  NVML queries
+        can stall for tens of ms next to a launch loop; if fewer than 3 samples landed inside the ~60 ms region, the window is
+        widened to the warm-up steps that ran back to back before it (same kernels, same load) and the line says so."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "not started"], "samples": 0}
         time.sleep(0.01)
@@ -112,13 +111,17 @@ class ClockSampler:
         except Exception:  # noqa: BLE001
             self.proc.kill()
         self.t.join(timeout=2)
-        rows = self.rows[first:]
+        rows = [r for r in self.rows if t_beg <= r[3] <= t_end]
+        window = "timed"
+        if len(rows) < 3:
+            rows = [r for r in self.rows if t_load <= r[3] <= t_end + 0.005]
+            window = "warmup+timed"
         bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
                 "hw_power_brake": 0x80}
         sm = sorted(r[0] for r in rows)
         reasons = sorted(n for n, bit in bits.items() if any(r[2] & bit for r in rows))
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx, "reasons": reasons,
-                "power_w_max": max((r[1] for r in rows), default=None), "samples": len(sm)}
+                "power_w_max": max((r[1] for r in rows), default=None), "samples": len(sm), "window": window}
 
 
 def cpu_reference_run(rank_k, sample_batch, iters, warmup, threads=None):
@@ -222,13 +225,14 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     with torch.no_grad():
-        for _ in range(args.warmup):
-            y = step(x_dev)
-        sync_all()
         sampler = ClockSampler(local)
         if rank == 0:
-            sampler.start()
-        s0 = sampler.mark()
+            sampler.start()                 # before the warm-up: the NVML process is up and sampling when the timed region starts
+        t_load = time.time()
+        for _ in range(max(args.warmup, 3)):
+            y = step(x_dev)
+        sync_all()
+        t_wall0 = time.time()
         n0 = B.launch_count()
         t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_beg.record()
@@ -236,10 +240,11 @@ def run_ours(args):
             y = step(x_dev, ev[s])
         t_end.record()
         sync_all()
+        t_wall1 = time.time()
         launches = B.launch_count() - n0
         ms = t_beg.elapsed_time(t_end)
         conv_ms = sum(a.elapsed_time(b) for row in ev for (a, b) in row)
-        clocks = sampler.stop(s0) if rank == 0 else None
+        clocks = sampler.stop(t_load, t_wall0, t_wall1) if rank == 0 else None
 
         # ---- end to end through the public API with HOST buffers: every step copies its (pinned) NCHW bf16 images
         # to the device, runs the trunk module (layout conversion included) and reads the result back to the host.

@@ -147,3 +147,20 @@ def test_lowrank1_pack_layout_cpu():
     h = layer.s_conv.h_conv.weight.detach().to(torch.bfloat16).float().reshape(C * M, d)
     cm = 70; u, e = divmod(cm - 64, 8); pos = (e // 4) * 32 + u * 4 + (e % 4)
     assert torch.equal(sp[1, :d, pos], v[cm]) and torch.equal(sp[1, d:, pos], h[cm])
+
+
+def test_lowrank1_fused_plan_cpu():
+    """The fused scheme-1 kernel's host-side plan (tile shape + shared-memory budget) is pure host code: the AlexNet layers of the
+    reference's config are covered, everything outside the documented envelope is refused (callers then take the unfused kernels)."""
+    from approx import backend as B
+    for (C, N, d, H) in [(64, 192, 5, 27), (192, 384, 3, 13), (384, 256, 3, 13), (256, 256, 3, 13)]:
+        for sep in (False, True):
+            assert B.lowrank1_fused_supported(64, H, H, C, N, 8, d, sep), (C, N, d, H, sep)
+    assert B.lowrank1_fused_supported(1, 7, 128, 8, 16, 8, 3, False)          # W = 128: one row per tile
+    assert not B.lowrank1_fused_supported(1, 7, 129, 8, 16, 8, 3, False)      # wider than a tile
+    assert not B.lowrank1_fused_supported(4, 13, 13, 64, 192, 8, 7, False)    # 7x7 bases: no instance
+    assert not B.lowrank1_fused_supported(4, 13, 13, 64, 192, 16, 3, False)   # M = 16: 4 channels per chunk < 16-byte TMA rows
+    assert not B.lowrank1_fused_supported(4, 13, 13, 12, 192, 8, 3, False)    # C % 8 != 0
+    assert not B.lowrank1_fused_supported(4, 13, 13, 64, 200, 8, 3, False)    # N % 16 != 0
+    assert not B.lowrank1_fused_supported(4, 13, 13, 64, 528, 8, 3, False)    # N > 512
+    assert not B.lowrank1_fused_supported(4, 13, 13, 64, 272, 8, 3, False)    # 256 < N, N % 32 != 0

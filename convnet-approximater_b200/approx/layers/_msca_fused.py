@@ -47,10 +47,6 @@ def _packed_chain(msca, cas, dtype):
     return _ops.cached(msca, "sd_chain", params, dtype, build)
 
 
-def parallel_forward(par, x):
-    return None
-
-
 def conv0_sd_forward(msca, x):
     """conv0 + sd_convs of an MSCA block as one kernel, or None."""
     mode = os.environ.get("CNA_MSCA_FUSED", "auto")
@@ -84,8 +80,6 @@ def conv0_sd_forward(msca, x):
                             [dw_w(c.conv2) for c in cas], [_ops.bias_f32(c.conv2) for c in cas],
                             ks, identity, res=None if fix is None else fix.res_f32())
     if not B.msca_sd_supported(msca.num_channel, 5, ks, x.dtype):
-        return None
-    if fix is not None and fix.p != max(ks) // 2 and False:
         return None
     w0, b0, w1, b1, w2, b2 = _packed_chain(msca, cas, x.dtype)
     return B.msca_sd(x.contiguous(), w0, b0, w1, b1, w2, b2, ks, identity, res=None if fix is None else fix.res_f32())

@@ -21,6 +21,7 @@ def _sig(params, dtype):
 
 def cached(owner: nn.Module, key, params, dtype, build):
     """Memoise `build()` on `owner`, keyed on the identity+version of `params`."""
+    _install_invalidation_hooks(owner)
     store = owner.__dict__.setdefault("_cna_cache", {})
     sig = _sig(params, dtype)
     hit = store.get(key)
@@ -29,6 +30,24 @@ def cached(owner: nn.Module, key, params, dtype, build):
     val = build()
     store[key] = (sig, val)
     return val
+
+
+def invalidate(module: nn.Module):
+    """Drop every packed / cast weight copy cached on `module` and its children.
+
+    The cache key is (data_ptr, Tensor._version), which `p.data.copy_()` / `.data.mul_()`-style in-place writes through
+    `.data` do NOT change (torch bumps no version counter there).  The reference's own flows assign `.weight.data = ...`
+    or copy under `no_grad` (both invalidate automatically); code that edits `.data` in place calls this, and it also
+    runs after every `load_state_dict` and `train()` / `eval()` switch of a module that owns a cache."""
+    for m in module.modules():
+        m.__dict__.pop("_cna_cache", None)
+
+
+def _install_invalidation_hooks(owner: nn.Module):
+    if owner.__dict__.get("_cna_hooked"):
+        return
+    owner.__dict__["_cna_hooked"] = True
+    owner.register_load_state_dict_post_hook(lambda mod, incompatible: invalidate(mod))
 
 
 def bias_f32(conv):

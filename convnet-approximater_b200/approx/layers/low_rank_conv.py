@@ -115,6 +115,10 @@ class _Scheme2Function(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, v_w, h_w, bias, mod):
+        if mod.fuse_relu or mod.fuse_pool:
+            # backward differentiates the plain h_conv(v_conv(x)): a fused ReLU mask / pool routing is not part of it
+            raise RuntimeError("LowRankExpConvV2: autograd through a layer with fuse_relu / fuse_pool set is not supported "
+                               "(inference-only epilogues); clear them or run under torch.no_grad()")
         H, W = x.shape[2:]
         c_pad = B.round_up(mod.in_channels, 16) if mod._fusable(x.dtype, H, W) else None
         xn = B.to_nhwc(x.detach(), c_pad)

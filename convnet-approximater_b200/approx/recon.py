@@ -32,6 +32,9 @@ class Scheme2Reconstructor:
         kh, kw = layer.kernel_size
         if layer.stride != (1, 1) or layer.padding != (kh // 2, kw // 2) or kh % 2 == 0 or kw % 2 == 0:
             raise NotImplementedError("reconstruction kernels cover stride-1 'same' convolutions")
+        if layer.fuse_relu or layer.fuse_pool:
+            # the gradients below are those of the plain h_conv(v_conv(x)) the reference fits (its teacher is the conv output)
+            raise ValueError("reconstruction differentiates the bare layer: clear fuse_relu / fuse_pool first")
         self.layer = layer
         self.lr, self.betas, self.eps, self.wd, self.l2_weight = lr, betas, eps, weight_decay, l2_weight
         self.group = process_group

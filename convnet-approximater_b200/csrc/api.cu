@@ -2,12 +2,33 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <mutex>
 
 namespace cna {
 static thread_local std::string g_err;
 static std::atomic<unsigned long long> g_launches{0};
 void set_error(const std::string& msg) { g_err = msg; }
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+int dev_info(DevInfo* out) {
+    constexpr int kMaxDev = 64;
+    static DevInfo cache[kMaxDev];
+    static bool have[kMaxDev] = {};
+    static std::mutex mu;
+    int dev = 0;
+    CNA_CUDA(cudaGetDevice(&dev));
+    CNA_CHECK(dev >= 0 && dev < kMaxDev, "device ordinal out of range");
+    std::lock_guard<std::mutex> lock(mu);
+    if (!have[dev]) {
+        DevInfo d{dev, 0, 0};
+        CNA_CUDA(cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev));
+        CNA_CUDA(cudaDeviceGetAttribute(&d.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        cache[dev] = d;
+        have[dev] = true;
+    }
+    *out = cache[dev];
+    return 0;
+}
 }  // namespace cna
 
 extern "C" {

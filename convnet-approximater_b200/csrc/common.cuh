@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 
 #include "../../include/cna_b200.h"
@@ -37,10 +38,49 @@ void count_launch(int n = 1);
         ::cna::count_launch();                                                          \
     } while (0)
 
+// Same check without counting (helpers whose caller counts the launch).
+#define CNA_LAUNCH_CHECK()                                                              \
+    do {                                                                                \
+        cudaError_t _e = cudaGetLastError();                                            \
+        if (_e != cudaSuccess) CNA_FAIL(std::string("kernel launch: ") + cudaGetErrorString(_e)); \
+    } while (0)
+
 // dwconv_tile.cu: register-tiled depthwise kernels for the MSCA shapes; *handled = false -> use the generic kernel
 int dw_tile_try(const void* x, const void* w_packed, const float* bias, const float* res, int res_p, const void* add, void* y,
                 int B, int H, int W, int Cin, int mult, int kh, int kw, int sh, int sw, int ph, int pw, int dtype, cudaStream_t st,
                 bool* handled);
+
+// ---- per-device state ----------------------------------------------------------------------------
+// One process may drive several GPUs (one host thread per device or cudaSetDevice round-robin): SM count, the opt-in
+// shared-memory limit and every cudaFuncSetAttribute are per DEVICE, so nothing below is cached process-wide.
+struct DevInfo { int dev, num_sms, max_smem; };
+// Properties of the CURRENT device (cached per ordinal, thread-safe).  Returns 0 / non-zero like the C ABI.
+int dev_info(DevInfo* out);
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize, applied once per (kernel instantiation, device): `done` is a per-call-site
+// bit mask over device ordinals (function-local static std::atomic<uint64_t>).
+template <typename KernelT>
+inline cudaError_t ensure_dyn_smem(KernelT kernel, int bytes, std::atomic<unsigned long long>& done) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
+}
+
+// Stream-ordered scratch that is released on every return path (the error macros return early).
+struct AsyncScratch {
+    void* ptr = nullptr;
+    cudaStream_t st = nullptr;
+    explicit AsyncScratch(cudaStream_t s) : st(s) {}
+    AsyncScratch(const AsyncScratch&) = delete;
+    AsyncScratch& operator=(const AsyncScratch&) = delete;
+    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&ptr, bytes, st); }
+    ~AsyncScratch() { if (ptr) cudaFreeAsync(ptr, st); }
+};
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -256,14 +256,11 @@ int cna_conv1x1_tc_forward(const void* a, const void* w_packed, const float* bia
     CNA_CHECK(a && w_packed && y && P > 0, "bad arguments");
     CNA_CHECK(cna_conv1x1_tc_supported(C, N), "configuration not supported (needs C%32==0, N%16==0, N<=256, W resident in smem)");
     CNA_CHECK(P < (1LL << 31) * 128LL, "too many pixels");
-    static int num_sms = 0, max_smem = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        CNA_CUDA(cudaGetDevice(&dev));
-        CNA_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        CNA_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-        CNA_CUDA(cudaFuncSetAttribute(conv1x1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    }
+    DevInfo di;
+    if (dev_info(&di)) return 1;
+    const int num_sms = di.num_sms, max_smem = di.max_smem;
+    static std::atomic<unsigned long long> attr_done{0};
+    CNA_CUDA(ensure_dyn_smem(conv1x1_tc_kernel, max_smem, attr_done));
     C1Params p{};
     p.P = P; p.C = C; p.N = N; p.nkc = C / kC1KC; p.relu = relu;
     p.ntiles = (int)((P + 127) / 128);

@@ -295,6 +295,7 @@ static int dw_strip_launch_t(const void* x, const void* w, const float* bias, co
         dw_strip_kernel<T, K, ALONG_W, true><<<grid, 256, 0, st>>>((const T*)x, (const T*)w, bias, res, res_p, (const T*)add, (T*)y, B, H, W, C, nitems);
     else        // the plain conv: no border-residue / running-sum code at all (predicated-off instructions still cost issue slots)
         dw_strip_kernel<T, K, ALONG_W, false><<<grid, 256, 0, st>>>((const T*)x, (const T*)w, bias, res, res_p, (const T*)add, (T*)y, B, H, W, C, nitems);
+    CNA_LAUNCH_CHECK();
     return 0;
 }
 
@@ -305,16 +306,14 @@ static int dw_tile_launch_t(const void* x, const void* w, const float* bias, con
     constexpr int XH = kDT + KH - 1, XW = kDT + KW - 1;
     const size_t smem = ((size_t)XH * XW + (size_t)KH * KW) * (kDC / 2) * 2 * sizeof(T);
     auto kern = dw_tile_kernel<T, KH, KW, ALONG_W>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CNA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};
+    CNA_CUDA(ensure_dyn_smem(kern, (int)smem, attr_done));
     const int tiles_h = ceil_div(H, kDT), tiles_w = ceil_div(W, kDT);
     const long long ntiles = (long long)B * tiles_h * tiles_w * (C / kDC);
     int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (216 * 1024) / (smem + 1024)));
     const int grid = (int)std::min<long long>(ntiles, 148LL * per_sm);
     kern<<<grid, 256, smem, st>>>((const T*)x, (const T*)w, bias, res, res_p, (const T*)add, (T*)y, B, H, W, C, tiles_h, tiles_w, ntiles);
+    CNA_LAUNCH_CHECK();
     return 0;
 }
 
@@ -324,13 +323,13 @@ static int dw_tile_dispatch(int kh, int kw, const void* x, const void* w, const 
     *handled = true;
     if (getenv("CNA_DW_NO_STRIP") == nullptr) {      // (diagnostic switch: use the smem-tiled kernel for strips too)
 #define CNA_STRIP_CASE(KV) \
-        if (kh == 1 && kw == KV && dw_strip_launch_t<T, KV, true>(x, w, bias, res, res_p, add, y, B, H, W, C, st) == 0) return 0; \
-        if (kw == 1 && kh == KV && dw_strip_launch_t<T, KV, false>(x, w, bias, res, res_p, add, y, B, H, W, C, st) == 0) return 0
-        CNA_STRIP_CASE(3);
-        CNA_STRIP_CASE(5);
-        CNA_STRIP_CASE(7);
-        CNA_STRIP_CASE(11);
-        CNA_STRIP_CASE(21);
+        if (kh == 1 && kw == KV) { const int rc = dw_strip_launch_t<T, KV, true>(x, w, bias, res, res_p, add, y, B, H, W, C, st); if (rc >= 0) return rc; } \
+        if (kw == 1 && kh == KV) { const int rc = dw_strip_launch_t<T, KV, false>(x, w, bias, res, res_p, add, y, B, H, W, C, st); if (rc >= 0) return rc; }
+        CNA_STRIP_CASE(3)
+        CNA_STRIP_CASE(5)
+        CNA_STRIP_CASE(7)
+        CNA_STRIP_CASE(11)
+        CNA_STRIP_CASE(21)
 #undef CNA_STRIP_CASE
     }
 #define CNA_DW_CASE(KHV, KWV) \

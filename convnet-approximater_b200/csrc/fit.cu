@@ -318,9 +318,10 @@ int cna_lowrank1_svd_fit(const float* W, int R, int q, int M, float* weights, fl
     CNA_CHECK(W && weights && bases && R > 0 && q > 0 && M > 0, "bad arguments");
     CNA_CHECK(q <= kSvdMax, "filter matrices with more than 64 columns (d > 8) are not supported yet");
     cudaStream_t st = as_stream(stream);
-    double *G = nullptr;
     size_t nG = (size_t)q * q;
-    CNA_CUDA(cudaMallocAsync(&G, (3 * nG + q) * sizeof(double), st));   // G | U | Vh | lam
+    AsyncScratch scratch(st);                                           // freed on every return path
+    CNA_CUDA(scratch.alloc((3 * nG + q) * sizeof(double)));             // G | U | Vh | lam
+    double* G = static_cast<double*>(scratch.ptr);
     double *U = G + nG, *Vh = U + nG, *lam = Vh + nG;
     CNA_CUDA(cudaMemsetAsync(G, 0, nG * sizeof(double), st));
     int rows_per_block = 1024;
@@ -334,7 +335,6 @@ int cna_lowrank1_svd_fit(const float* W, int R, int q, int M, float* weights, fl
     int grid = (int)std::min<long long>(ceil_div_ll(total, 256), 148LL * 16);
     lowrank1_factors_kernel<<<grid, 256, 0, st>>>(W, Vh, lam, weights, bases, R, q, M);
     CNA_LAUNCH_OK();
-    CNA_CUDA(cudaFreeAsync(G, st));
     return 0;
 }
 
@@ -346,10 +346,12 @@ int cna_svd_jacobi_large(const float* A, int m, int n, int r, float* U, float* S
     CNA_CHECK(A && U && S && Vh, "null pointer");
     CNA_CHECK(m >= n && n >= 1 && r >= 1 && r <= n, "need 1 <= r <= n <= m (transpose on the caller side otherwise)");
     cudaStream_t st = as_stream(stream);
-    double *Wk = nullptr; int* d_rot = nullptr;
     const size_t nW = (size_t)n * m, nV = (size_t)n * n;
-    CNA_CUDA(cudaMallocAsync(&Wk, (nW + nV + n) * sizeof(double), st));
-    CNA_CUDA(cudaMallocAsync(&d_rot, sizeof(int) * (n + 1), st));
+    AsyncScratch s_w(st), s_rot(st);                                    // freed on every return path
+    CNA_CUDA(s_w.alloc((nW + nV + n) * sizeof(double)));
+    CNA_CUDA(s_rot.alloc(sizeof(int) * (n + 1)));
+    double* Wk = static_cast<double*>(s_w.ptr);
+    int* d_rot = static_cast<int*>(s_rot.ptr);
     double *Vk = Wk + nW, *sv = Vk + nV;
     int* d_order = d_rot + 1;
     jacobi_init_kernel<<<148 * 4, 256, 0, st>>>(A, Wk, Vk, m, n);
@@ -381,8 +383,6 @@ int cna_svd_jacobi_large(const float* A, int m, int n, int r, float* U, float* S
     jacobi_gather_kernel<<<r, 256, 0, st>>>(Wk, Vk, sv, d_order, U, S, Vh, m, n, r);
     CNA_LAUNCH_OK();
     CNA_CUDA(cudaStreamSynchronize(st));   // `order` (host) must outlive the copy
-    CNA_CUDA(cudaFreeAsync(Wk, st));
-    CNA_CUDA(cudaFreeAsync(d_rot, st));
     return 0;
 }
 

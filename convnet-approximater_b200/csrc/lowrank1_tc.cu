@@ -639,11 +639,8 @@ static size_t l1_plan(L1Params& p, int B, int H, int W, int C, int N, int M, int
 template <int D, int M, bool SEP, bool HRUN>
 static int l1_launch(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const float* s_packed, const float* d_bias, void* y,
                      const L1Params& p, size_t smem, int grid, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        CNA_CUDA(cudaFuncSetAttribute(lowrank1_fused_kernel<D, M, SEP, HRUN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};
+    CNA_CUDA(ensure_dyn_smem(lowrank1_fused_kernel<D, M, SEP, HRUN>, 227 * 1024, attr_done));
     lowrank1_fused_kernel<D, M, SEP, HRUN><<<grid, kL1Threads, smem, st>>>(tm_x, tm_w, s_packed, d_bias, (__nv_bfloat16*)y, p);
     CNA_LAUNCH_OK();
     return 0;
@@ -667,12 +664,9 @@ int cna_lowrank1_fused_forward(const void* x, const float* s_packed, const void*
     const size_t smem = l1_plan(p, B, H, W, C, N, M, d, separable, 227 * 1024);
     CNA_CHECK(smem != 0, "configuration not covered by the fused scheme-1 kernel (bf16, stride 1, 'same' padding, d in {3,5}, "
                          "M in {4,8}, C*M % 64 == 0, C % 8 == 0, N % 16 == 0, N <= 512, W <= 128)");
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        CNA_CUDA(cudaGetDevice(&dev));
-        CNA_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    DevInfo di;
+    if (dev_info(&di)) return 1;
+    const int num_sms = di.num_sms;
     CUtensorMap tm_x, tm_w;
     {
         cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};

@@ -664,11 +664,8 @@ using namespace cna;
 template <int CKV, int KPV, int NT2V>
 static int lr2_launch_one(int grid, size_t smem, int max_smem, cudaStream_t st, const CUtensorMap& tm_x, const CUtensorMap& tm_wv,
                           const CUtensorMap& tm_wh, const CUtensorMap& tm_y, const float* bias, const LR2Params& p) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        CNA_CUDA(cudaFuncSetAttribute(lowrank2_fused_kernel<CKV, KPV, NT2V>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        attr_set = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};
+    CNA_CUDA(ensure_dyn_smem(lowrank2_fused_kernel<CKV, KPV, NT2V>, max_smem, attr_done));
     lowrank2_fused_kernel<CKV, KPV, NT2V><<<grid, kThreads, smem, st>>>(tm_x, tm_wv, tm_wh, tm_y, bias, p);
     return 0;
 }
@@ -699,13 +696,9 @@ static int lr2_launch(const void* x, const void* wv_packed, const void* wh_packe
     CNA_CHECK(axis == 0 || t_only, "axis 1 is only available for the 3-tap convolution");
     CNA_CHECK(shape_ok(H, W, c_pad, k_pad, N, d), "configuration not supported by the fused kernel "
               "(needs d=3, c_pad%16==0, k_pad in {16,32,64}, N%64==0)");
-    static int num_sms = 0, max_smem = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        CNA_CUDA(cudaGetDevice(&dev));
-        CNA_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        CNA_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    }
+    DevInfo di;
+    if (dev_info(&di)) return 1;
+    const int num_sms = di.num_sms, max_smem = di.max_smem;
     const int CK = pick_ck(c_pad), NT2 = pick_nt2(N);
     const int KH = axis == 0 ? H : W, KW = axis == 0 ? W : H;      // dims along the kernel's tile-row / tile-col axes
     LR2Params p{};

@@ -196,14 +196,11 @@ int cna_wgrad3_tc(const void* a, const void* bm, float* dw, int B, int H, int W,
     CNA_CHECK(ca_stride >= 8 && ca_stride % 8 == 0 && Ca >= 1 && Ca <= ca_stride, "wide tensor: channel stride must be a multiple of 8");
     CNA_CHECK(kb_stride >= 8 && kb_stride % 8 == 0 && kb_stride <= 64 && kb >= 1 && kb <= kb_stride, "narrow tensor: at most 64 channels");
     CNA_CHECK(axis == 0 || axis == 1, "axis must be 0 or 1");
-    static int num_sms = 0, max_smem = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        CNA_CUDA(cudaGetDevice(&dev));
-        CNA_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        CNA_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-        CNA_CUDA(cudaFuncSetAttribute(wgrad3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    }
+    DevInfo di;
+    if (dev_info(&di)) return 1;
+    const int num_sms = di.num_sms, max_smem = di.max_smem;
+    static std::atomic<unsigned long long> attr_done{0};
+    CNA_CUDA(ensure_dyn_smem(wgrad3_tc_kernel, max_smem, attr_done));
     WgParams p{};
     // 64-channel sub-blocks, rounded up to whole 128-channel M-blocks: channels past the tensor's extent are TMA zero fill
     const int nsub_total = 2 * ((ca_stride + 127) / 128);

@@ -40,6 +40,15 @@ _SIGS = {
     "cna_lowrank2_fused_forward_t": "ppppppiiiiiiiip",
     "cna_tapconv3_tc_forward": "pppiiiiiip",
     "cna_wgrad3_tc": "pppiiiiiiiiip",
+    "cna_wgrad3_tc_acc": "pppiiiiiiiiip",
+    "cna_l2_recon_loss_grad_bias_acc": "ppppppiiLfip",
+    "cna_peer_alloc": "Lpp",
+    "cna_peer_open": "pp",
+    "cna_peer_close": "p",
+    "cna_peer_free": "p",
+    "cna_recon_sync_header_bytes": "",
+    "cna_recon_sync_step": "piiLLLppppppiffffffp",
+    "cna_recon_sync_error": "pp",
     "cna_bias_grad": "ppLiip",
     "cna_dwconv_wgrad": "pppiiiiiiiiiip",
     "cna_dwconv_dgrad": "pppiiiiiiiiiip",
@@ -57,8 +66,8 @@ _SIGS = {
     "cna_l2_recon_loss_grad_bias": "ppppppiiLfip",
     "cna_conv_taps_wgrad": "ppppiiiiiiiiip",
     "cna_pack_taps_weight_dgrad": "ppiiiip",
-    "cna_adamw_step": "ppppLfffffifp",
-    "cna_adamw_step_dev": "ppppLfffffpfp",
+    "cna_adamw_step": "ppppLLfffffifp",
+    "cna_adamw_step_dev": "ppppLLfffffpfp",
     "cna_lowrank1_svd_fit": "piiippp",
     "cna_msca_equiv_kernel": "pppppiipppp",
 }
@@ -435,51 +444,62 @@ def lowrank2_fused_traced(x, wv, wh, bias, tiles=32, relu=False):
     return y, trace
 
 
-def lowrank2_fused_with_t(x, wv, wh, bias, relu=False):
-    """Like lowrank2_fused, also returning the bf16 intermediate T = v_conv(x), (B,H,W,k_pad), written by the same kernel."""
+def lowrank2_fused_with_t(x, wv, wh, bias, relu=False, out=None):
+    """Like lowrank2_fused, also returning the bf16 intermediate T = v_conv(x), (B,H,W,k_pad), written by the same kernel.
+    `out` = (y, t) pre-allocated buffers (CUDA-graph capture: fixed addresses)."""
     _ready(x)
     B, H, W, cp = x.shape
     d, kp, cp2 = wv.shape
     N = wh.shape[1]
     assert cp == cp2 and x.dtype == torch.bfloat16 and x.is_contiguous()
-    y = torch.empty((B, H, W, N), device=x.device, dtype=torch.bfloat16)
-    t = torch.empty((B, H, W, kp), device=x.device, dtype=torch.bfloat16)
+    if out is not None:
+        y, t = out
+        assert y.shape == (B, H, W, N) and t.shape == (B, H, W, kp) and y.is_contiguous() and t.is_contiguous()
+    else:
+        y = torch.empty((B, H, W, N), device=x.device, dtype=torch.bfloat16)
+        t = torch.empty((B, H, W, kp), device=x.device, dtype=torch.bfloat16)
     with torch.cuda.device(x.device):
         _check(lib().cna_lowrank2_fused_forward_t(_p(x), _p(wv), _p(wh), _p(bias), _p(y), _p(t), B, H, W, cp, kp, N, d, int(relu), _stream(x)))
     return y, t
 
 
-def tapconv3_tc(x, w_packed, axis):
+def tapconv3_tc(x, w_packed, axis, out=None):
     """3-tap 'same' conv on tcgen05: x (B,H,W,c_pad) bf16, w_packed [3][k_pad][c_pad] bf16 -> (B,H,W,k_pad) bf16; taps along H (axis 0) or W (1)."""
     _ready(x)
     B, H, W, cp = x.shape
     d, kp, cp2 = w_packed.shape
     assert d == 3 and cp == cp2 and x.dtype == torch.bfloat16 and x.is_contiguous() and w_packed.dtype == torch.bfloat16
-    out = torch.empty((B, H, W, kp), device=x.device, dtype=torch.bfloat16)
+    if out is None:
+        out = torch.empty((B, H, W, kp), device=x.device, dtype=torch.bfloat16)
+    assert out.shape == (B, H, W, kp) and out.is_contiguous()
     with torch.cuda.device(x.device):
         _check(lib().cna_tapconv3_tc_forward(_p(x), _p(w_packed), _p(out), B, H, W, cp, kp, int(axis), _stream(x)))
     return out
 
 
-def wgrad3_tc(a, bm, dw, Ca, kb, axis, wide_is_input):
+def wgrad3_tc(a, bm, dw, Ca, kb, axis, wide_is_input, accumulate=False):
     """Writes the 3-tap conv weight gradient into fp32 `dw` (reference OIHW layout) on tcgen05.
-    a (B,H,W,ca_stride) bf16 = the wide tensor (x or dL/dy), bm (B,H,W,kb_stride<=64) bf16 = the narrow one (dL/dT or T)."""
+    a (B,H,W,ca_stride) bf16 = the wide tensor (x or dL/dy), bm (B,H,W,kb_stride<=64) bf16 = the narrow one (dL/dT or T).
+    accumulate=True adds into `dw` (the caller zeroed it) instead of overwriting it."""
     _ready(a)
     B, H, W, cs = a.shape
     ks = bm.shape[3]
     assert bm.shape[:3] == a.shape[:3] and a.dtype == bm.dtype == torch.bfloat16 and a.is_contiguous() and bm.is_contiguous()
     assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == Ca * kb * 3
+    fn = lib().cna_wgrad3_tc_acc if accumulate else lib().cna_wgrad3_tc
     with torch.cuda.device(a.device):
-        _check(lib().cna_wgrad3_tc(_p(a), _p(bm), _p(dw), B, H, W, cs, int(Ca), ks, int(kb), int(axis), int(wide_is_input), _stream(a)))
+        _check(fn(_p(a), _p(bm), _p(dw), B, H, W, cs, int(Ca), ks, int(kb), int(axis), int(wide_is_input), _stream(a)))
     return dw
 
 
-def adamw_step_dev_(p, g, m, v, step_dev, lr, betas, eps, wd, grad_scale=1.0):
-    """Graph-capturable fused AdamW: `step_dev` is a 1-element int32 device tensor counting the steps taken."""
+def adamw_step_dev_(p, g, m, v, step_dev, lr, betas, eps, wd, grad_scale=1.0, n_decay=None):
+    """Graph-capturable fused AdamW: `step_dev` is a 1-element int32 device tensor counting the steps taken.
+    Weight decay covers the first `n_decay` elements (default: all)."""
     _ready(p)
     assert step_dev.dtype == torch.int32 and step_dev.numel() == 1
+    nd = p.numel() if n_decay is None else int(n_decay)
     with torch.cuda.device(p.device):
-        _check(lib().cna_adamw_step_dev(_p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(betas[0]), float(betas[1]), float(eps),
+        _check(lib().cna_adamw_step_dev(_p(p), _p(g), _p(m), _p(v), p.numel(), nd, float(lr), float(betas[0]), float(betas[1]), float(eps),
                                         float(wd), _p(step_dev), float(grad_scale), _stream(p)))
     return p
 
@@ -660,6 +680,20 @@ def l2_recon(y_new, y_old, scale, want_grad=True, db=None):
     return norms, g
 
 
+def l2_recon_into(y_new, y_old, scale, sumsq, norms, g, db):
+    """Loss / gradient / bias-gradient kernels of `l2_recon` on caller-owned buffers, WITHOUT zeroing `sumsq` (B,) and `db` (N,):
+    a multi-layer step zeroes them with one memset for all layers.  Capturable in a CUDA graph (no allocation)."""
+    _ready(y_new)
+    Bn = y_new.shape[0]
+    per = y_new.numel() // Bn
+    assert y_new.shape == y_old.shape == g.shape and y_new.is_contiguous() and y_old.is_contiguous() and g.is_contiguous()
+    assert sumsq.numel() == Bn and norms.numel() == Bn and db.dtype == torch.float32 and db.numel() == y_new.shape[-1]
+    with torch.cuda.device(y_new.device):
+        _check(lib().cna_l2_recon_loss_grad_bias_acc(_p(y_new), _p(y_old), _p(sumsq), _p(norms), _p(g), _p(db), y_new.shape[-1], Bn,
+                                                     per, float(scale), dtype_code(y_new.dtype), _stream(y_new)))
+    return norms
+
+
 def conv_taps_wgrad(x, g, taps, axis, pad, dw_out=None, db_out=None, want_bias=False):
     """x (B,H,W,C), g (B,H,W,N) NHWC -> dw (N,C,taps) fp32 [, db (N,) fp32] for a stride-1 'same' tap conv."""
     _ready(x)
@@ -689,12 +723,15 @@ def pack_taps_dgrad(w, dtype):
 
 
 def adamw_step_(param, grad, exp_avg, exp_avg_sq, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
-                grad_scale=1.0):
+                grad_scale=1.0, n_decay=None):
+    """Weight decay covers the first `n_decay` elements (default: all) — biases go last and get none, as in the reference's
+    timm-built optimizer."""
     _ready(param)
     for t in (param, grad, exp_avg, exp_avg_sq):
         assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == param.numel()
+    nd = param.numel() if n_decay is None else int(n_decay)
     with torch.cuda.device(param.device):
-        _check(lib().cna_adamw_step(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), float(lr),
+        _check(lib().cna_adamw_step(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), nd, float(lr),
                                     float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step),
                                     float(grad_scale), _stream(param)))
     return param

@@ -61,10 +61,6 @@ class ParallelConv(nn.Module):
     def forward_nhwc(self, x, res=None):
         """Running sum in the reference's order ((b0 + b1) + b2 ... + x); `res` (FixPaddingBias) is applied
         by the caller on the finished sum."""
-        from . import _msca_fused
-        fused = _msca_fused.parallel_forward(self, x)
-        if fused is not None:
-            return fused
         acc = None
         for br in self.cascades():
             acc = br.forward_nhwc(x, add=acc)

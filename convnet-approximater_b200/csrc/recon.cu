@@ -197,13 +197,13 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const T* __restrict__ g,
 }
 
 __global__ void __launch_bounds__(256) adamw_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                                       float* __restrict__ v, long long n, float lr, float beta1, float beta2,
+                                                       float* __restrict__ v, long long n, long long n_decay, float lr, float beta1, float beta2,
                                                        float eps, float wd, const int* __restrict__ step_dev, float gscale) {
     const float step = (float)(*step_dev + 1);
     const float bc1 = 1.f - powf(beta1, step), bc2 = 1.f - powf(beta2, step);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float gi = g[i] * gscale;
-        float pi = p[i] * (1.f - lr * wd);
+        float pi = p[i] * (1.f - lr * (i < n_decay ? wd : 0.f));
         float mi = beta1 * m[i] + (1.f - beta1) * gi;
         float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
         m[i] = mi; v[i] = vi;
@@ -227,11 +227,11 @@ __global__ void pack_taps_dgrad_kernel(const float* __restrict__ w, T* __restric
 
 // decoupled weight decay Adam (torch.optim.AdamW semantics), fp32 master parameters
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                                   float* __restrict__ v, long long n, float lr, float beta1, float beta2,
+                                                   float* __restrict__ v, long long n, long long n_decay, float lr, float beta1, float beta2,
                                                    float eps, float wd, float bc1, float bc2, float gscale) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float gi = g[i] * gscale;
-        float pi = p[i] * (1.f - lr * wd);
+        float pi = p[i] * (1.f - lr * (i < n_decay ? wd : 0.f));
         float mi = beta1 * m[i] + (1.f - beta1) * gi;
         float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
         m[i] = mi; v[i] = vi;
@@ -247,12 +247,12 @@ using namespace cna;
 extern "C" {
 
 static int l2_recon_impl(const void* y_new, const void* y_old, float* sumsq_scratch, float* norms, void* grad, float* dbias, int N,
-                         int B, long long per_sample, float scale, int dtype, void* stream) {
+                         int B, long long per_sample, float scale, int dtype, void* stream, bool zero_first = true) {
     CNA_CHECK(y_new && y_old && sumsq_scratch && norms, "null pointer");
     CNA_CHECK(B > 0 && B <= 65535 && per_sample > 0, "bad dims");
     CNA_CHECK(dbias == nullptr || (grad != nullptr && N > 0 && per_sample % N == 0), "bias gradient needs the gradient tensor and N");
     cudaStream_t st = as_stream(stream);
-    CNA_CUDA(cudaMemsetAsync(sumsq_scratch, 0, sizeof(float) * B, st));
+    if (zero_first) CNA_CUDA(cudaMemsetAsync(sumsq_scratch, 0, sizeof(float) * B, st));
     const bool aligned = ((reinterpret_cast<uintptr_t>(y_new) | reinterpret_cast<uintptr_t>(y_old) | reinterpret_cast<uintptr_t>(grad)) & 15) == 0;
     if (dtype == CNA_BF16 && per_sample % 8 == 0 && aligned) {
         const long long ps8 = per_sample / 8;
@@ -269,7 +269,7 @@ static int l2_recon_impl(const void* y_new, const void* y_old, float* sumsq_scra
         l2_sumsq_v8_kernel<<<grid, 256, 0, st>>>((const uint4*)y_new, (const uint4*)y_old, sumsq_scratch, ps8);
         CNA_LAUNCH_OK();
         if (grad) {
-            if (fuse_db) CNA_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * N, st));
+            if (fuse_db && zero_first) CNA_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * N, st));
             l2_grad_v8_kernel<<<grid, 256, fuse_db ? sizeof(float) * N : 0, st>>>((const uint4*)y_new, (const uint4*)y_old, sumsq_scratch, norms,
                                                                                 (uint4*)grad, ps8, scale, fuse_db ? dbias : nullptr, N8);
             CNA_LAUNCH_OK();
@@ -301,6 +301,14 @@ int cna_l2_recon_loss_grad_bias(const void* y_new, const void* y_old, float* sum
                                 int N, int B, long long per_sample, float scale, int dtype, void* stream) {
     CNA_CHECK(dbias != nullptr, "null pointer");
     return l2_recon_impl(y_new, y_old, sumsq_scratch, norms, grad, dbias, N, B, per_sample, scale, dtype, stream);
+}
+
+/* Same as cna_l2_recon_loss_grad_bias, but sumsq_scratch and dbias must have been zeroed by the caller (one memset for all layers of a
+ * multi-layer reconstruction step instead of two per layer). */
+int cna_l2_recon_loss_grad_bias_acc(const void* y_new, const void* y_old, float* sumsq_scratch, float* norms, void* grad, float* dbias,
+                                    int N, int B, long long per_sample, float scale, int dtype, void* stream) {
+    CNA_CHECK(dbias != nullptr, "null pointer");
+    return l2_recon_impl(y_new, y_old, sumsq_scratch, norms, grad, dbias, N, B, per_sample, scale, dtype, stream, false);
 }
 
 int cna_conv_taps_wgrad(const void* x, const void* g, float* dw, float* dbias, int B, int H, int W, int C, int N,
@@ -356,12 +364,12 @@ int cna_pack_taps_weight_dgrad(const float* w_oit, void* packed, int O, int I, i
     return 0;
 }
 
-int cna_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+int cna_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, long long n_decay, float lr, float beta1,
                    float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream) {
-    CNA_CHECK(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "bad arguments");
+    CNA_CHECK(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1 && n_decay >= 0, "bad arguments");
     float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
     int grid = (int)std::min<long long>(ceil_div_ll(n, 256), 148LL * 8);
-    adamw_kernel<<<grid, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
+    adamw_kernel<<<grid, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, n_decay, lr, beta1, beta2, eps, weight_decay,
                                                      bc1, bc2, grad_scale);
     CNA_LAUNCH_OK();
     return 0;
@@ -369,11 +377,11 @@ int cna_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_a
 
 /* Graph-capturable AdamW: the step counter lives on the device (bias corrections are computed in the kernel from *step_dev + 1,
  * a second one-thread kernel then increments it), so a captured reconstruction step stays correct across replays. */
-int cna_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+int cna_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, long long n_decay, float lr, float beta1,
                        float beta2, float eps, float weight_decay, int* step_dev, float grad_scale, void* stream) {
-    CNA_CHECK(param && grad && exp_avg && exp_avg_sq && step_dev && n > 0, "bad arguments");
+    CNA_CHECK(param && grad && exp_avg && exp_avg_sq && step_dev && n > 0 && n_decay >= 0, "bad arguments");
     int grid = (int)std::min<long long>(ceil_div_ll(n, 256), 148LL * 8);
-    adamw_dev_kernel<<<grid, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
+    adamw_dev_kernel<<<grid, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, n_decay, lr, beta1, beta2, eps, weight_decay,
                                                          step_dev, grad_scale);
     CNA_LAUNCH_OK();
     bump_step_kernel<<<1, 1, 0, as_stream(stream)>>>(step_dev);

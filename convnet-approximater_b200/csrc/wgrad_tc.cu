@@ -189,9 +189,8 @@ using namespace cna;
 
 extern "C" {
 
-/* dw (fp32, reference OIHW layout, overwritten) of a 3-tap 'same' conv, see include/cna_b200.h */
-int cna_wgrad3_tc(const void* a, const void* bm, float* dw, int B, int H, int W, int ca_stride, int Ca, int kb_stride, int kb, int axis,
-                  int wide_is_input, void* stream) {
+static int wgrad3_impl(const void* a, const void* bm, float* dw, int B, int H, int W, int ca_stride, int Ca, int kb_stride, int kb, int axis,
+                       int wide_is_input, bool zero_first, void* stream) {
     CNA_CHECK(a && bm && dw && B > 0 && H > 0 && W > 0, "bad arguments");
     CNA_CHECK(ca_stride >= 8 && ca_stride % 8 == 0 && Ca >= 1 && Ca <= ca_stride, "wide tensor: channel stride must be a multiple of 8");
     CNA_CHECK(kb_stride >= 8 && kb_stride % 8 == 0 && kb_stride <= 64 && kb >= 1 && kb <= kb_stride, "narrow tensor: at most 64 channels");
@@ -224,11 +223,23 @@ int cna_wgrad3_tc(const void* a, const void* bm, float* dw, int B, int H, int W,
     CUtensorMap tm_a, tm_b;
     if (wg_encode(&tm_a, a, ca_stride, B, H, W, axis, 10)) return 1;
     if (wg_encode(&tm_b, bm, kb_stride, B, H, W, axis, 8)) return 1;
-    CNA_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Ca * kb * 3, as_stream(stream)));
+    if (zero_first) CNA_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Ca * kb * 3, as_stream(stream)));
     dim3 grid((unsigned)std::min(p.ntiles, std::max(1, num_sms / p.groups)), (unsigned)p.groups);
     wgrad3_tc_kernel<<<grid, kWgThreads, smem, as_stream(stream)>>>(tm_a, tm_b, dw, p);
     CNA_LAUNCH_OK();
     return 0;
+}
+
+/* dw (fp32, reference OIHW layout, overwritten) of a 3-tap 'same' conv, see include/cna_b200.h */
+int cna_wgrad3_tc(const void* a, const void* bm, float* dw, int B, int H, int W, int ca_stride, int Ca, int kb_stride, int kb, int axis,
+                  int wide_is_input, void* stream) {
+    return wgrad3_impl(a, bm, dw, B, H, W, ca_stride, Ca, kb_stride, kb, axis, wide_is_input, true, stream);
+}
+
+/* same, ACCUMULATING into dw (the caller zeroed it: one memset for the flat gradient buffer of all layers) */
+int cna_wgrad3_tc_acc(const void* a, const void* bm, float* dw, int B, int H, int W, int ca_stride, int Ca, int kb_stride, int kb, int axis,
+                      int wide_is_input, void* stream) {
+    return wgrad3_impl(a, bm, dw, B, H, W, ca_stride, Ca, kb_stride, kb, axis, wide_is_input, false, stream);
 }
 
 }  // extern "C"

@@ -237,13 +237,57 @@ int cna_bias_grad(const void* g, float* dbias, long long P, int N, int dtype, vo
  * C=O, N=I, pad = taps-1-pad to get dL/dx from dL/dy. */
 int cna_pack_taps_weight_dgrad(const float* w_oit, void* packed, int O, int I, int taps, int dtype, void* stream);
 /* Fused AdamW (torch.optim.AdamW semantics) on a flat fp32 buffer; grad is multiplied by grad_scale first
- * (1/world_size after an all-reduce(SUM)).  Replaces optimizer.step() at src/approx/hooks/finetune.py:331. */
-int cna_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+ * (1/world_size after an all-reduce(SUM)).  Weight decay applies to the first n_decay elements only: the reference builds its
+ * optimizer with timm's create_optimizer_v2 (src/approx/hooks/finetune.py:188), whose default filter gives biases no decay, so
+ * callers lay the flat buffer out as [weights | biases] and pass n_decay = number of weight elements (n_decay = n: uniform decay).
+ * Replaces optimizer.step() at src/approx/hooks/finetune.py:331. */
+int cna_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, long long n_decay, float lr, float beta1,
                    float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
 /* Same, with the step counter on the device (*step_dev holds the number of steps taken so far and is incremented): the call is
  * CUDA-graph capturable, so a whole reconstruction step can be replayed without host work. */
-int cna_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+int cna_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, long long n_decay, float lr, float beta1,
                        float beta2, float eps, float weight_decay, int* step_dev, float grad_scale, void* stream);
+
+/* Accumulating variants for a multi-layer reconstruction step (one memset of the flat gradient buffer instead of several per layer):
+ * cna_wgrad3_tc_acc adds into dw; cna_l2_recon_loss_grad_bias_acc expects sumsq_scratch and dbias zeroed by the caller. */
+int cna_wgrad3_tc_acc(const void* a, const void* bm, float* dw, int B, int H, int W, int ca_stride, int Ca, int kb_stride, int kb, int axis,
+                      int wide_is_input, void* stream);
+int cna_l2_recon_loss_grad_bias_acc(const void* y_new, const void* y_old, float* sumsq_scratch, float* norms, void* grad, float* dbias,
+                                    int N, int B, long long per_sample, float scale, int dtype, void* stream);
+
+/* ---- peer memory + fused gradient exchange / optimizer step (multi-GPU reconstruction) -------------------------------
+ * Replaces DistributedDataParallel's gradient all-reduce inside total_loss.backward() and the optimizer.step() that follows it
+ * (src/approx/hooks/finetune.py:153-160, 329-331) by ONE kernel over NVLink peer memory.
+ *
+ * cna_peer_alloc: cudaMalloc + zero a "symmetric" buffer on the current device and export its CUDA-IPC handle (64 bytes, host).
+ * cna_peer_open : map another process' buffer from its handle (peer access is enabled lazily); cna_peer_close unmaps it.
+ * Every rank allocates the same layout:  [header, cna_recon_sync_header_bytes() bytes: barrier flags, zero-initialised]
+ *                                        [off_grad : n fp32 gradients]  [off_param : n fp32 parameters]
+ *
+ * cna_recon_sync_step (all ranks launch it once per step, after their gradient kernels, on `stream`):
+ *   barrier A over the peers' flags; rank r sums slice r = [r*ceil(n/4/world)*4, ...) of all `world` gradient buffers in rank
+ *   order, runs AdamW (torch semantics, grad * grad_scale first, no weight decay on bias elements) on that slice with ITS slice of
+ *   exp_avg / exp_avg_sq (sharded optimizer state, indexed like the flat buffer), writes the new fp32 parameters into EVERY
+ *   rank's parameter region; barrier B; then every rank re-packs all parameters into the bf16 operand buffers of the fused
+ *   kernels and the fp32 bias vectors.  *step_dev (device int, steps taken so far) is read for the bias correction / barrier epoch
+ *   and incremented: the launch is CUDA-graph capturable.
+ *   Flat layout, per layer l (contiguous, in order): v_conv.weight (K,C,3,1) | h_conv.weight (N,K,1,3) | h_conv.bias (N);
+ *     layer_offsets_host[4l..] = {off_v, off_h, off_b, end} in floats, layer_dims_host[5l..] = {K, C, N, k_pad, c_pad},
+ *     layer_ptrs_host[4l..] = {wv [3][k_pad][c_pad] bf16, wh [3][N][k_pad] bf16, wd [3][k_pad][N] bf16 (h_conv transposed, taps
+ *     flipped: the weight of the data-gradient conv), bias fp32 (N)} — device pointers whose padding the caller zeroed once.
+ *   peers_host[r] = base of rank r's symmetric buffer as mapped in THIS process (peers_host[rank] = the local allocation).
+ *   n % 4 == 0; world <= 8; nlayers <= 16.  A barrier that sees no progress for ~2 s sets an error word instead of hanging:
+ *   cna_recon_sync_error reads it back (0 = fine). */
+int cna_peer_alloc(long long bytes, void** ptr_out, unsigned char* handle64_host);
+int cna_peer_open(const unsigned char* handle64_host, void** ptr_out);
+int cna_peer_close(void* ptr);
+int cna_peer_free(void* ptr);
+int cna_recon_sync_header_bytes(void);
+int cna_recon_sync_step(void* const* peers_host, int rank, int world, long long n, long long off_grad, long long off_param,
+                        float* exp_avg, float* exp_avg_sq, int* step_dev, const long long* layer_offsets_host,
+                        const int* layer_dims_host, void* const* layer_ptrs_host, int nlayers, float lr, float beta1, float beta2,
+                        float eps, float weight_decay, float grad_scale, void* stream);
+int cna_recon_sync_error(const void* local_buffer, int* err_host);
 
 /* 2x2/stride-2 max pool, NHWC (VGG trunk glue between the approximated convs). */
 int cna_maxpool2x2(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream);

@@ -42,6 +42,7 @@ _SIGS = {
     "cna_wgrad3_tc": "pppiiiiiiiiip",
     "cna_wgrad3_tc_acc": "pppiiiiiiiiip",
     "cna_l2_recon_loss_grad_bias_acc": "ppppppiiLfip",
+    "cna_l2_norm_backward": "pppppiLip",
     "cna_peer_alloc": "Lpp",
     "cna_peer_open": "pp",
     "cna_peer_close": "p",
@@ -678,6 +679,20 @@ def l2_recon(y_new, y_old, scale, want_grad=True, db=None):
             _check(lib().cna_l2_recon_loss_grad(_p(y_new), _p(y_old), _p(scratch), _p(norms), _p(g), Bn, per, float(scale),
                                                 dtype_code(y_new.dtype), _stream(y_new)))
     return norms, g
+
+
+def l2_norm_backward(y_new, y_old, norms, upstream):
+    """g[b] = (y_new[b] - y_old[b]) * upstream[b] / norms[b] (0 where the norm is 0); same memory layout as y_new."""
+    _ready(y_new)
+    assert y_new.shape == y_old.shape and y_new.dtype == y_old.dtype and y_new.is_contiguous() and y_old.is_contiguous()
+    Bn = y_new.shape[0]
+    up = upstream.detach().to(torch.float32).contiguous()
+    assert norms.dtype == torch.float32 and norms.numel() == Bn and up.numel() == Bn
+    g = torch.empty_like(y_new)
+    with torch.cuda.device(y_new.device):
+        _check(lib().cna_l2_norm_backward(_p(y_new), _p(y_old), _p(norms), _p(up), _p(g), Bn, y_new.numel() // Bn,
+                                          dtype_code(y_new.dtype), _stream(y_new)))
+    return g
 
 
 def l2_recon_into(y_new, y_old, scale, sumsq, norms, g, db):

@@ -18,6 +18,8 @@
 // partial sum) is rounded to bf16 at the same point, so results track the reference's bf16 modules.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace cna {
 
 constexpr int SD_THREADS = 256;
@@ -366,6 +368,13 @@ static size_t sd_smem_bytes(const SdParams& p, int cb) {
 
 }  // namespace cna
 
+namespace cna {
+// msca16.cu: the 16-row-march generation of this kernel (-1 = configuration not covered)
+int msca_sd16_launch(const void* x, void* y, const float* w0, const float* b0, const float* w1cat, const float* b1cat,
+                     const float* w2cat, const float* b2cat, const float* res, int res_p, const int* ks_host, int nb, int identity,
+                     int B, int H, int W, int C, int dtype, cudaStream_t st);
+}
+
 using namespace cna;
 
 extern "C" {
@@ -387,6 +396,14 @@ int cna_msca_sd_forward(const void* x, void* y, const float* w0, const float* b0
     CNA_CHECK(cna_msca_sd_supported(C, 5, nb, ks_host, dtype), "configuration not supported by the fused sd kernel");
     CNA_CHECK(res == nullptr || res_p > 0, "res without res_p");
     CNA_CHECK(B <= 65535, "batch too large for grid.y");
+    {
+        static const bool old_only = [] { const char* e = getenv("CNA_MSCA_SD"); return e && e[0] == 'o'; }();   // diagnostic A/B switch
+        if (!old_only) {
+            const int rc = msca_sd16_launch(x, y, w0, b0, w1cat, b1cat, w2cat, b2cat, res, res_p, ks_host, nb, identity, B, H, W, C, dtype,
+                                            as_stream(stream));
+            if (rc >= 0) return rc;
+        }
+    }
     SdParams p{};
     p.B = B; p.H = H; p.W = W; p.C = C; p.nb = nb; p.identity = identity; p.res_p = res ? res_p : 0;
     for (int i = 0; i < nb; ++i) p.ks[i] = ks_host[i];

@@ -29,7 +29,7 @@ namespace cna {
 
 constexpr int kPeerMax = 8;
 constexpr int kReconMaxLayers = 16;
-constexpr int kSyncThreads = 256;
+constexpr int kSyncThreads = 1024;     // one block per SM (all blocks spin in the barriers, so all must be resident)
 // header of a symmetric buffer (bytes): flags A [16] | flags B [16] | local block counter | error word | pad  -> 1024
 constexpr int kHdrBytes = 1024;
 constexpr int kOffFlagA = 0, kOffFlagB = 64, kOffCount = 128, kOffErr = 132;
@@ -113,10 +113,14 @@ recon_sync_kernel(const __grid_constant__ ReconSyncParams p) {
     const float inv_sqrt_bc2 = rsqrtf(bc2), step_size = p.lr / bc1;
     const float4* myparam = reinterpret_cast<const float4*>(me + p.off_param);
     for (long long i4 = lo4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i4 < hi4; i4 += (long long)gridDim.x * blockDim.x) {
+        float4 pv4[kPeerMax];
+#pragma unroll
+        for (int r = 0; r < kPeerMax; ++r)                        // all peer loads in flight before the first add (NVLink latency once)
+            pv4[r] = r < p.world ? ld_volatile_f4(reinterpret_cast<const float4*>(p.peer[r] + p.off_grad) + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
         float g[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int r = 0; r < p.world; ++r) {                       // fixed order: every rank would compute the same bits
-            const float4 v = ld_volatile_f4(reinterpret_cast<const float4*>(p.peer[r] + p.off_grad) + i4);
-            g[0] += v.x; g[1] += v.y; g[2] += v.z; g[3] += v.w;
+#pragma unroll
+        for (int r = 0; r < kPeerMax; ++r) {                      // fixed rank order: every rank would compute the same bits
+            if (r < p.world) { g[0] += pv4[r].x; g[1] += pv4[r].y; g[2] += pv4[r].z; g[3] += pv4[r].w; }
         }
         const float4 pv = myparam[i4];
         float4 mv = reinterpret_cast<const float4*>(p.exp_avg)[i4], vv = reinterpret_cast<const float4*>(p.exp_avg_sq)[i4];
@@ -155,25 +159,30 @@ recon_sync_kernel(const __grid_constant__ ReconSyncParams p) {
     }
     wait_flags(flagB, p.world, epoch, err);
 
-    // ---- phase 2: re-pack ALL parameters (every rank needs all operand buffers) from the local fp32 copy
+    // ---- phase 2: re-pack ALL parameters (every rank needs all operand buffers) from the local fp32 copy.
+    // Destination-ordered: consecutive threads write consecutive bf16 elements of a pack buffer (coalesced stores) and gather the
+    // fp32 source (L2-resident, 12-byte stride); padded rows / columns of the packs were zeroed once by the caller and are skipped.
     const volatile float* param = reinterpret_cast<const volatile float*>(me + p.off_param);
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
-        const int l = find_layer(p, i);
+    const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x, gstride = (long long)gridDim.x * blockDim.x;
+    for (int l = 0; l < p.nlayers; ++l) {
         const ReconLayerDesc& L = p.layer[l];
-        if (i >= L.end) continue;                                  // alignment padding after the last layer
-        const float w = param[i];
-        if (i < L.off_h) {                                         // v_conv.weight (K, C, 3, 1)
-            const long long j = i - L.off_v;
-            const int t = (int)(j % 3), c = (int)((j / 3) % L.C), k = (int)(j / (3LL * L.C));
-            L.wv[((size_t)t * L.kp + k) * L.cp + c] = __float2bfloat16_rn(w);
-        } else if (i < L.off_b) {                                  // h_conv.weight (N, K, 1, 3)
-            const long long j = i - L.off_h;
-            const int t = (int)(j % 3), k = (int)((j / 3) % L.K), nn = (int)(j / (3LL * L.K));
-            const __nv_bfloat16 b = __float2bfloat16_rn(w);
-            L.wh[((size_t)t * L.N + nn) * L.kp + k] = b;
-            L.wd[((size_t)(2 - t) * L.kp + k) * L.N + nn] = b;     // data-gradient conv: taps flipped, channels transposed
-        } else {
-            L.bias[i - L.off_b] = w;
+        const long long nv = 3LL * L.K * L.C, nh = 3LL * L.N * L.K;
+        for (long long d = gtid; d < nv + 2 * nh + L.N; d += gstride) {
+            if (d < nv) {                                          // wv[t][k][c] <- v_conv.weight[k][c][t]
+                const int c = (int)(d % L.C), k = (int)((d / L.C) % L.K), t = (int)(d / ((long long)L.C * L.K));
+                L.wv[((size_t)t * L.kp + k) * L.cp + c] = __float2bfloat16_rn(param[L.off_v + ((long long)k * L.C + c) * 3 + t]);
+            } else if (d < nv + nh) {                              // wh[t][n][k] <- h_conv.weight[n][k][t]
+                const long long e = d - nv;
+                const int k = (int)(e % L.K), nn = (int)((e / L.K) % L.N), t = (int)(e / ((long long)L.K * L.N));
+                L.wh[((size_t)t * L.N + nn) * L.kp + k] = __float2bfloat16_rn(param[L.off_h + ((long long)nn * L.K + k) * 3 + t]);
+            } else if (d < nv + 2 * nh) {                          // wd[t][k][n] <- h_conv.weight[n][k][2 - t]  (data-gradient conv)
+                const long long e = d - nv - nh;
+                const int nn = (int)(e % L.N), k = (int)((e / L.N) % L.K), t = (int)(e / ((long long)L.N * L.K));
+                L.wd[((size_t)t * L.kp + k) * L.N + nn] = __float2bfloat16_rn(param[L.off_h + ((long long)nn * L.K + k) * 3 + (2 - t)]);
+            } else {
+                const long long e = d - nv - 2 * nh;
+                L.bias[e] = param[L.off_b + e];
+            }
         }
     }
 }

@@ -53,6 +53,19 @@ __global__ void __launch_bounds__(256) l2_grad_kernel(const T* __restrict__ yn, 
         g[off + i] = from_f32<T>((to_f32(ldg(yn + off + i)) - to_f32(ldg(yo + off + i))) * f);
 }
 
+// Backward of the per-sample norm for autograd callers: g[b] = (y_new[b] - y_old[b]) * upstream[b] / norms[b]   (0 where norm = 0)
+template <typename T>
+__global__ void __launch_bounds__(256) l2_norm_backward_kernel(const T* __restrict__ yn, const T* __restrict__ yo,
+                                                              const float* __restrict__ norms, const float* __restrict__ upstream,
+                                                              T* __restrict__ g, long long per_sample) {
+    const int b = blockIdx.y;
+    const float nrm = norms[b];
+    const float f = nrm > 0.f ? upstream[b] / nrm : 0.f;
+    const size_t off = (size_t)b * per_sample;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_sample; i += (long long)gridDim.x * blockDim.x)
+        g[off + i] = from_f32<T>((to_f32(ldg(yn + off + i)) - to_f32(ldg(yo + off + i))) * f);
+}
+
 // ---- bf16, 16-byte vectorised variants (per_sample % 8 == 0): the reconstruction step's loss kernels move 3 passes over y, so
 // they are plain HBM streams and want 128-bit accesses; the gradient kernel also accumulates the BIAS gradient
 // (db[n] = sum_p g[p][n]) when the grid stride is a multiple of N, so no separate pass over g is needed. ----
@@ -309,6 +322,19 @@ int cna_l2_recon_loss_grad_bias_acc(const void* y_new, const void* y_old, float*
                                     int N, int B, long long per_sample, float scale, int dtype, void* stream) {
     CNA_CHECK(dbias != nullptr, "null pointer");
     return l2_recon_impl(y_new, y_old, sumsq_scratch, norms, grad, dbias, N, B, per_sample, scale, dtype, stream, false);
+}
+
+int cna_l2_norm_backward(const void* y_new, const void* y_old, const float* norms, const float* upstream, void* grad, int B,
+                         long long per_sample, int dtype, void* stream) {
+    CNA_CHECK(y_new && y_old && norms && upstream && grad, "null pointer");
+    CNA_CHECK(B > 0 && B <= 65535 && per_sample > 0, "bad dims");
+    dim3 grid((unsigned)std::min<long long>(ceil_div_ll(per_sample, 256 * 8), 148 * 4), B);
+    cudaStream_t st = as_stream(stream);
+    if (dtype == CNA_F32) l2_norm_backward_kernel<float><<<grid, 256, 0, st>>>((const float*)y_new, (const float*)y_old, norms, upstream, (float*)grad, per_sample);
+    else if (dtype == CNA_BF16) l2_norm_backward_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)y_new, (const __nv_bfloat16*)y_old, norms, upstream, (__nv_bfloat16*)grad, per_sample);
+    else CNA_FAIL("unsupported dtype");
+    CNA_LAUNCH_OK();
+    return 0;
 }
 
 int cna_conv_taps_wgrad(const void* x, const void* g, float* dw, float* dbias, int B, int H, int W, int C, int N,

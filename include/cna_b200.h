@@ -248,6 +248,11 @@ int cna_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_a
 int cna_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, long long n_decay, float lr, float beta1,
                        float beta2, float eps, float weight_decay, int* step_dev, float grad_scale, void* stream);
 
+/* Backward of the per-sample output-L2 norm for autograd callers (the loss hook get_l2_error, src/approx/hooks/finetune.py:80-82,
+ * reached from total_loss.backward() at :329): grad[b] = (y_new[b] - y_old[b]) * upstream[b] / norms[b], 0 where the norm is 0. */
+int cna_l2_norm_backward(const void* y_new, const void* y_old, const float* norms, const float* upstream, void* grad, int B,
+                         long long per_sample, int dtype, void* stream);
+
 /* Accumulating variants for a multi-layer reconstruction step (one memset of the flat gradient buffer instead of several per layer):
  * cna_wgrad3_tc_acc adds into dw; cna_l2_recon_loss_grad_bias_acc expects sumsq_scratch and dbias zeroed by the caller. */
 int cna_wgrad3_tc_acc(const void* a, const void* bm, float* dw, int B, int H, int W, int ca_stride, int Ca, int kb_stride, int kb, int axis,

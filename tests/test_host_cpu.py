@@ -164,3 +164,50 @@ def test_lowrank1_fused_plan_cpu():
     assert not B.lowrank1_fused_supported(4, 13, 13, 64, 200, 8, 3, False)    # N % 16 != 0
     assert not B.lowrank1_fused_supported(4, 13, 13, 64, 528, 8, 3, False)    # N > 512
     assert not B.lowrank1_fused_supported(4, 13, 13, 64, 272, 8, 3, False)    # 256 < N, N % 32 != 0
+
+
+def test_hook_registry_holds_the_reference_names_and_signatures():
+    """approx.hooks: the names the shipped configs use, with the reference's constructor arguments (src/approx/hooks/*.py)."""
+    import inspect
+    from approx.hooks import HOOK, Hook, build_hook, get_priority, Priority
+    want = {
+        "InferenceTimeHook": ["runner", "priority", "infer_cfg"],
+        "Fps": ["runner", "priority", "repeat_times", "log_interval", "num_workers", "use_torch_benchmark", "dataset_args", "data_config"],
+        "L2Reconstruct": ["runner", "priority", "asym", "l2_weight", "cls_weight", "epoch_behavior", "no_norm", "dataset_args",
+                          "optim_args", "sche_args", "data_config", "other_args"],
+        "LowRankExpV1Decomp": ["runner", "priority"],
+        "CkptHook": ["runner", "priority", "ckpt_cfg"],
+        "ModelAnalysis": ["runner", "priority", "input_shape"],
+    }
+    for name, args in want.items():
+        cls = HOOK.get(name)
+        assert issubclass(cls, Hook)
+        got = list(inspect.signature(cls.__init__).parameters)[1:]
+        assert got[:len(args)] == args, (name, got)
+    assert Hook.stages == ('before_run', 'after_register', 'after_initialize', 'after_optimize', 'after_run')
+    assert get_priority("normal") == 50 and get_priority(Priority.HIGH) == 30 and get_priority(7) == 7
+    import pytest
+    with pytest.raises(ValueError):
+        get_priority(101)
+
+    class R:        # minimal runner stand-in
+        model = None
+    h = build_hook(dict(type="LowRankExpV1Decomp", priority="LOW"), runner=R())
+    assert h.priority == 70 and h.name == "LowRankExpV1Decomp"
+    from approx.utils.general import is_method_overridden
+    assert is_method_overridden("after_run", Hook, h) and not is_method_overridden("before_run", Hook, h)
+
+
+def test_synthetic_loader_and_lr_schedule():
+    import torch
+    from approx.hooks._common import SyntheticLoader
+    from approx.hooks.finetune import _schedule
+    from approx.hooks._common import ArgTable, DEFAULT_SCHED_ARGS
+    ld = SyntheticLoader(3, (3, 8, 8), num_batches=2, num_classes=5, device="cpu")
+    a = [(x.clone(), t.clone()) for x, t in ld]
+    b = [(x.clone(), t.clone()) for x, t in ld]
+    assert len(a) == len(ld) == 2 and a[0][0].shape == (3, 3, 8, 8) and int(a[0][1].max()) < 5
+    assert all(torch.equal(p[0], q[0]) and torch.equal(p[1], q[1]) for p, q in zip(a, b))      # every epoch sees the same batches
+    assert _schedule(ArgTable(DEFAULT_SCHED_ARGS), 1e-3)(7) == 1e-3
+    cos = _schedule(ArgTable(DEFAULT_SCHED_ARGS, dict(sched='cosine', epochs=10, min_lr=1e-5)), 1e-3)
+    assert abs(cos(0) - 1e-3) < 1e-12 and abs(cos(10) - 1e-5) < 1e-12 and cos(5) < cos(1)

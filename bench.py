@@ -356,8 +356,13 @@ def run_ours(args):
     # device-resident input, NHWC with the 3 image channels zero-padded to 16 (TMA needs 16-byte rows)
     x_dev = torch.zeros(Bsz, 224, 224, 16, device=dev, dtype=torch.bfloat16)
     x_dev[..., :3] = torch.randn(Bsz, 224, 224, 3, device=dev).bfloat16()
-    # host-side input for the end-to-end leg: what a user of the reference API holds (NCHW bf16, pinned)
-    x_host = torch.randn(Bsz, 3, 224, 224).bfloat16().pin_memory()
+    # host-side input for the end-to-end leg: what an image loader holds — uint8 NCHW batches in pinned memory, exactly what the
+    # reference's timm loaders ship to the GPU before normalising there (hooks/fps.py:38-49); --e2e-input bf16 sends ready-made
+    # bf16 tensors instead (2 bytes per value over PCIe)
+    if args.e2e_input == "u8":
+        x_host = torch.randint(0, 256, (Bsz, 3, 224, 224), dtype=torch.uint8).pin_memory()
+    else:
+        x_host = torch.randn(Bsz, 3, 224, 224).bfloat16().pin_memory()
     y_host = torch.empty(Bsz, 512, 7, 7, dtype=torch.bfloat16).pin_memory()
 
     convs = trunk.conv_layers()
@@ -495,7 +500,9 @@ def run_ours(args):
                        "layers": 13, "l2": "inputs/activations per step (>=411 MB) exceed the 126 MB L2; no flush needed",
                        "parallelism": f"batch-sharded x{world}, no collective"},
             "e2e": {"value": world * Bsz * args.steps / (e2e_ms * 1e-3), "unit": "images/s",
-                    "h2d_bytes_per_step": x_host.numel() * 2, "d2h_bytes_per_step": y_host.numel() * 2},
+                    "h2d_bytes_per_step": x_host.numel() * x_host.element_size(), "d2h_bytes_per_step": y_host.numel() * 2,
+                    "input": ("uint8 NCHW images in pinned host memory, normalised on the device in the layout kernel (the reference's "
+                              "timm prefetch-loader path)" if args.e2e_input == "u8" else "bf16 NCHW tensors in pinned host memory")},
             "gpu_launches": int(launches),
             "roofline": ({"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak}
                          if bound == "hbm" else
@@ -547,6 +554,7 @@ def main():
     ap.add_argument("--rank", type=int, default=64)
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-input", default="u8", choices=["u8", "bf16"], help="host-side input of the end-to-end leg")
     ap.add_argument("--no-msca", action="store_true", help="skip the MSCA (config 4) sub-record")
     ap.add_argument("--no-recon", action="store_true", help="skip the reconstruction (config 3) sub-record")
     ap.add_argument("--no-lib", action="store_true", help="skip the torch/cuDNN library baseline of the trunk")

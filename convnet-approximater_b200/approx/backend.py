@@ -23,6 +23,7 @@ _SIGS = {
     "cna_device_check": "",
     "cna_nchw_to_nhwc": "ppiiiiiiip",
     "cna_nhwc_to_nchw": "ppiiiiiiip",
+    "cna_u8_nchw_to_nhwc_norm": "ppppiiiiip",
     "cna_pack_taps_weight": "ppiiiiiip",
     "cna_pack_dw_weight": "ppiiiip",
     "cna_conv_taps_forward": "pppppiiiiiiiiiiiip",
@@ -71,6 +72,7 @@ _SIGS = {
     "cna_adamw_step_dev": "ppppLLfffffpfp",
     "cna_lowrank1_svd_fit": "piiippp",
     "cna_msca_equiv_kernel": "pppppiipppp",
+    "cna_lowrank1_alt_fit": "piiipppiiDiipipp",
 }
 
 
@@ -86,7 +88,7 @@ def lib():
         for name, sig in _SIGS.items():
             fn = getattr(L, name)
             fn.restype = c_int
-            fn.argtypes = [{"p": c_void_p, "i": c_int, "L": ctypes.c_longlong, "f": ctypes.c_float}[ch] for ch in sig]
+            fn.argtypes = [{"p": c_void_p, "i": c_int, "L": ctypes.c_longlong, "f": ctypes.c_float, "D": ctypes.c_double}[ch] for ch in sig]
         L.cna_last_error.restype = ctypes.c_char_p
         L.cna_launch_count.restype = ctypes.c_ulonglong
         L.cna_version.restype = c_int
@@ -159,6 +161,18 @@ def to_nhwc(x: torch.Tensor, c_pad: int | None = None, dtype=None) -> torch.Tens
     with torch.cuda.device(x.device):
         _check(lib().cna_nchw_to_nhwc(_p(x), _p(out), B, C, H, W, c_pad, dtype_code(x.dtype), dtype_code(dtype),
                                       _stream(x)))
+    return out
+
+
+def u8_to_nhwc_norm(x_u8: torch.Tensor, mean255: torch.Tensor, inv_std255: torch.Tensor, c_pad: int = 16) -> torch.Tensor:
+    """uint8 (B,C,H,W) images -> normalised bf16 (B,H,W,c_pad): (x - mean255[c]) * inv_std255[c], padding channels zero."""
+    _ready(x_u8)
+    assert x_u8.dtype == torch.uint8 and x_u8.dim() == 4 and x_u8.is_contiguous()
+    Bn, C, H, W = x_u8.shape
+    assert mean255.dtype == inv_std255.dtype == torch.float32 and mean255.numel() == inv_std255.numel() == C
+    out = torch.empty((Bn, H, W, c_pad), device=x_u8.device, dtype=torch.bfloat16)
+    with torch.cuda.device(x_u8.device):
+        _check(lib().cna_u8_nchw_to_nhwc_norm(_p(x_u8), _p(out), _p(mean255), _p(inv_std255), Bn, C, H, W, c_pad, _stream(x_u8)))
     return out
 
 
@@ -619,6 +633,26 @@ def lowrank1_svd_fit(W2d: torch.Tensor, M: int):
     return weights, bases
 
 
+def lowrank1_alt_fit(W2d, d, weights, bases, lmda_list, max_iter, epsilon=1e-3, mm_rounds=6, fista_iters=40):
+    """Alternating nuclear-norm fit on the device (cna_lowrank1_alt_fit).  W2d (R, d*d); weights (R, M) and bases (M, d*d) are the
+    starting point and are updated IN PLACE.  Returns the objective trace (after every B-step and A-step)."""
+    _ready(W2d)
+    R, q = W2d.shape
+    M = bases.shape[0]
+    assert q == d * d and weights.shape == (R, M) and bases.shape == (M, q)
+    for t in (W2d, weights, bases):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.device == W2d.device
+    lm = (ctypes.c_double * len(lmda_list))(*[float(v) for v in lmda_list])
+    cap = 2 * len(lmda_list) * max_iter
+    trace = (ctypes.c_double * cap)()
+    n = c_int(0)
+    with torch.cuda.device(W2d.device):
+        _check(lib().cna_lowrank1_alt_fit(_p(W2d), R, int(d), M, _p(weights), _p(bases), ctypes.cast(lm, c_void_p), len(lmda_list),
+                                          int(max_iter), float(epsilon), int(mm_rounds), int(fista_iters), ctypes.cast(trace, c_void_p),
+                                          cap, ctypes.cast(ctypes.byref(n), c_void_p), _stream(W2d)))
+    return [trace[i] for i in range(n.value)]
+
+
 def msca_equiv_kernel(w1s, b1s, w2s, b2s):
     """Lists over branches of conv1.weight (C,1,1,k), conv1.bias (C,)|None, conv2.weight (C,1,k,1), conv2.bias."""
     _ready(w1s[0])
@@ -682,12 +716,13 @@ def l2_recon(y_new, y_old, scale, want_grad=True, db=None):
 
 
 def l2_norm_backward(y_new, y_old, norms, upstream):
-    """g[b] = (y_new[b] - y_old[b]) * upstream[b] / norms[b] (0 where the norm is 0); same memory layout as y_new."""
+    """g[b] = (y_new[b] - y_old[b]) * upstream[b] / norms[b] (0 where the norm is 0); same memory layout as y_new.
+    y_old=None reads as zero, norms=None as one: g[b] = y_new[b] * upstream[b]."""
     _ready(y_new)
-    assert y_new.shape == y_old.shape and y_new.dtype == y_old.dtype and y_new.is_contiguous() and y_old.is_contiguous()
+    assert y_new.is_contiguous() and (y_old is None or (y_new.shape == y_old.shape and y_new.dtype == y_old.dtype and y_old.is_contiguous()))
     Bn = y_new.shape[0]
     up = upstream.detach().to(torch.float32).contiguous()
-    assert norms.dtype == torch.float32 and norms.numel() == Bn and up.numel() == Bn
+    assert (norms is None or (norms.dtype == torch.float32 and norms.numel() == Bn)) and up.numel() == Bn
     g = torch.empty_like(y_new)
     with torch.cuda.device(y_new.device):
         _check(lib().cna_l2_norm_backward(_p(y_new), _p(y_old), _p(norms), _p(up), _p(g), Bn, y_new.numel() // Bn,

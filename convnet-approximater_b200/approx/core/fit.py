@@ -40,6 +40,38 @@ def scheme1_svd(W: torch.Tensor, M: int):
     return s_w.to(home), d_w.to(home)
 
 
+def scheme1_init(W: torch.Tensor, M: int, init_method: str = 'svd', generator=None):
+    """Starting point (weights (N*C, M), bases (M, d*d)) of the scheme-1 fit, on the device (reference core/low_rank_exp.py:98-125):
+    'svd'      weights = U[:, :M] * sqrt(S[:M]),  bases = sqrt(S[:M]) * Vh[:M]     (truncated SVD of the (N*C) x d^2 filter matrix)
+    'standard' weights = the first min(M, d^2) columns of the filter matrix, bases = the matching unit vectors
+    'random'   both uniform in [0, 1)."""
+    N, C, d = W.shape[:3]
+    q = d * d
+    W2 = _dev(W.detach()).to(torch.float32).reshape(N * C, q).contiguous()
+    if init_method == 'svd':
+        weights, bases = B.lowrank1_svd_fit(W2, M)
+    elif init_method == 'standard':
+        upb = min(M, q)
+        weights = torch.zeros(N * C, M, device=W2.device)
+        weights[:, :upb] = W2[:, :upb]
+        bases = torch.zeros(M, q, device=W2.device)
+        bases[torch.arange(upb), torch.arange(upb)] = 1.0
+    elif init_method == 'random':
+        weights = torch.rand(N * C, M, device=W2.device, generator=generator)
+        bases = torch.rand(M, q, device=W2.device, generator=generator)
+    else:
+        raise AssertionError(f"Not supported init method: {init_method}")
+    return W2, weights.contiguous(), bases.contiguous()
+
+
+def scheme1_writeback(weights: torch.Tensor, bases: torch.Tensor, N: int, C: int, d: int, home):
+    """(weights (N*C, M), bases (M, d*d)) -> s_conv.weight (C*M,1,d,d), d_conv.weight (N,C*M,1,1) (reference :181-184)."""
+    M = bases.shape[0]
+    s_w = bases.reshape(1, M, d, d).expand(C, -1, -1, -1).reshape(C * M, 1, d, d).contiguous()
+    d_w = weights.reshape(N, C * M, 1, 1).contiguous()
+    return s_w.to(home), d_w.to(home)
+
+
 def pc_energy(bases: torch.Tensor) -> float:
     """Mean share of each basis' energy in its leading singular value (logged at low_rank_exp.py:177-180)."""
     _, s, _ = B.svd_small(_dev(bases.detach()))

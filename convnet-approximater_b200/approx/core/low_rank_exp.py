@@ -56,19 +56,31 @@ class LowRankExpV1(Approximater):
         sub.new_module.bias.data = sub.old_module.bias.data
 
     def optimize(self, sub: Substitution):
+        """Reference core/low_rank_exp.py:139-184.  The starting point (`init_method`) IS the result when max_iter = 0 (every shipped
+        *_svd_* config); with max_iter > 0 the alternating nuclear-norm fit the reference delegates to cvxpy runs on the device
+        (csrc/altfit.cu) over the same lambda schedule, iteration cap and stopping rule."""
         if self.init_decomp:
             return
-        if self.init_method != 'svd':
-            raise NotImplementedError(f"init_method={self.init_method!r}: only the 'svd' initialisation runs on the device")
-        if self.max_iter > 0 and len(self.lmda_list) > 0:
-            raise NotImplementedError(
-                "the cvxpy alternating nuclear-norm fit (reference core/low_rank_exp.py:160-176) has no device "
-                "implementation yet; use max_iter=0 (truncated-SVD fit, as in every shipped *_svd_* config)")
         src, tgt = sub.old_module, sub.new_module
-        s_w, d_w = fit.scheme1_svd(src.weight.data, tgt.num_base)
-        d = src.weight.shape[2]
-        for _ in self.lmda_list:   # the reference logs the energy once per penalty value
-            _log().info(f"PC Energy = {fit.pc_energy(s_w[:tgt.num_base].reshape(tgt.num_base, d, d))}")
+        W = src.weight.data
+        N, C, d = W.shape[:3]
+        assert W.shape[3] == d, "the reference assumes square kernels (core/low_rank_exp.py:149)"
+        M = tgt.num_base
+        W2, weights, bases = fit.scheme1_init(W, M, self.init_method)
+        log = _log()
+        if self.max_iter > 0 and len(self.lmda_list) > 0:
+            log.info(f"lambda list: {self.lmda_list}")
+            from approx import backend as B
+            for lmda in self.lmda_list:          # one call per lambda so the principal-component energy can be logged like the reference
+                trace = B.lowrank1_alt_fit(W2, d, weights, bases, [float(lmda)], self.max_iter, self.epsilon)
+                for i, f in enumerate(trace):
+                    log.info(f"[lamda: {lmda}]({i // 2 + 1}/{self.max_iter})[{i % 2 + 1}], total error: {f}")
+                log.info(f"PC Energy = {fit.pc_energy(bases.reshape(M, d, d))}")
+            self.last_trace = trace
+        else:
+            for _ in self.lmda_list:             # the reference logs the energy once per penalty value
+                log.info(f"PC Energy = {fit.pc_energy(bases.reshape(M, d, d))}")
+        s_w, d_w = fit.scheme1_writeback(weights, bases, N, C, d, W.device)
         tgt.s_conv.weight.data = s_w
         tgt.d_conv.weight.data = d_w
 

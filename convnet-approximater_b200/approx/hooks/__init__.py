@@ -8,9 +8,9 @@ instead of torch ops, a synthetic loader when no dataset library is installed (t
 """
 from .hook import build_hook, Hook, HOOK
 from .priority import Priority, get_priority
-from .measure import InferenceTimeHook, Fps, ModelAnalysis
+from .measure import InferenceTimeHook, Fps, ModelAnalysis, ClassEvalHook
 from .finetune import L2Reconstruct
 from .misc import LowRankExpV1Decomp, CkptHook
 
-__all__ = ["build_hook", "Hook", "HOOK", "Priority", "get_priority", "InferenceTimeHook", "Fps", "ModelAnalysis",
+__all__ = ["build_hook", "Hook", "HOOK", "Priority", "get_priority", "InferenceTimeHook", "Fps", "ModelAnalysis", "ClassEvalHook",
            "L2Reconstruct", "LowRankExpV1Decomp", "CkptHook"]

@@ -54,15 +54,17 @@ class _L2Norm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y_new, y_old):
         a, b, cl = _same_layout(y_new.detach(), y_old.detach().to(y_new.dtype))
-        norms, _ = B.l2_recon(a, b, 1.0, want_grad=False)
-        ctx.save_for_backward(a, b, norms)
+        # the unit gradient (y_new - y_old) / norm is produced with the norms and saved INSTEAD of y_new: the layers that follow a
+        # replaced conv in the reference's models are in-place (nn.ReLU(inplace=True)) and overwrite y_new before backward runs
+        norms, unit = B.l2_recon(a, b, 1.0, want_grad=True)
+        ctx.save_for_backward(unit)
         ctx.cl = cl
         return norms
 
     @staticmethod
     def backward(ctx, gn):
-        a, b, norms = ctx.saved_tensors
-        g = B.l2_norm_backward(a, b, norms, gn)
+        (unit,) = ctx.saved_tensors
+        g = B.l2_norm_backward(unit, None, None, gn)
         return (g.permute(0, 3, 1, 2) if ctx.cl else g), None
 
 
@@ -131,7 +133,7 @@ class FusedAdamW:
             if p.dtype == torch.float32 and p.is_contiguous():
                 B.adamw_step_(p.data.view(-1), g, it["m"], it["v"], it["steps"], lr, self.betas, self.eps, self.wd,
                               n_decay=p.numel() if it["decay"] else 0)
-                p.data = p.data                       # new version counter value: packed-weight caches refresh
+                torch.autograd.graph.increment_version(p)      # the kernel wrote through the raw pointer: packed-weight caches key on _version
             else:
                 if it["master"] is None:
                     it["master"] = p.detach().to(torch.float32).contiguous().view(-1).clone()

@@ -186,3 +186,53 @@ class ModelAnalysis(Hook):
         macs, params = count_macs_params(model, self.input_shape)
         self.result = dict(macs=macs, params=params)
         log().info(f"Model Macs: {macs / 1e9:.3f} GMac, Params: {params / 1e6:.3f} M")
+
+
+@HOOK.register_module()
+class ClassEvalHook(Hook):
+    """after_run: top-1 / top-5 / loss of the finished model on the validation split (reference hooks/class_eval_hook.py:58-68,
+    classification/validate.py).  eval_cfg keys of the reference that matter here: dataset, data, batch_size, input_size, mean, std,
+    interpolation, crop_pct.  Without a dataset library (timm is not a dependency of this backend) the hook evaluates on the synthetic
+    loader and SAYS SO: the accuracies are then meaningless, the images/s figure is not."""
+
+    def __init__(self, runner, priority, eval_cfg):
+        super().__init__(runner, priority)
+        cfg = dict(batch_size=128, input_size=(3, 224, 224), dataset='', data='path/to/dataset', mean=(0.485, 0.456, 0.406),
+                   std=(0.229, 0.224, 0.225), interpolation='bicubic', crop_pct=0.875, num_batches=8, num_classes=1000)
+        cfg.update(eval_cfg)
+        self.eval_cfg = cfg
+        self.result = None
+
+    def after_run(self):
+        cfg = self.eval_cfg
+        ds = ArgTable(dict(name=cfg['dataset'], root=cfg['data'], batch_size=cfg['batch_size'], num_batches=cfg['num_batches'],
+                           num_classes=cfg['num_classes']))
+        dc = ArgTable(DEFAULT_DATA_CONFIG, dict(input_size=cfg['input_size'], mean=cfg['mean'], std=cfg['std'],
+                                                interpolation=cfg['interpolation'], crop_pct=cfg['crop_pct']))
+        synthetic = False
+        try:
+            loader = make_loader('validation', ds, dc, dict(num_workers=cfg.get('workers', 4)))
+        except RuntimeError as e:
+            log().warning(f"ClassEvalHook: {e}; evaluating on SYNTHETIC data — accuracy numbers below are meaningless")
+            ds['name'] = 'synthetic'
+            loader = make_loader('validation', ds, dc, None)
+            synthetic = True
+        model = self.runner.model.cuda().eval()
+        loss_fn = nn.CrossEntropyLoss()
+        n, top1, top5, loss_sum = 0, 0, 0, 0.0
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        with torch.no_grad():
+            for inp, target in loader:
+                inp, target = inp.cuda(), target.cuda()
+                out = model(inp).float()
+                target = target.clamp_max(out.shape[1] - 1)
+                loss_sum += float(loss_fn(out, target)) * inp.size(0)
+                hit = out.topk(min(5, out.shape[1]), dim=1).indices.eq(target.view(-1, 1))
+                top1 += int(hit[:, :1].sum()); top5 += int(hit.sum()); n += inp.size(0)
+        b.record()
+        torch.cuda.synchronize()
+        n = max(n, 1)
+        self.result = dict(top1=100.0 * top1 / n, top5=100.0 * top5 / n, loss=loss_sum / n, images=n,
+                           images_per_s=n / a.elapsed_time(b) * 1e3, synthetic=synthetic or ds['name'] in ('', 'synthetic'))
+        log().info(f"ClassEval: {self.result}")

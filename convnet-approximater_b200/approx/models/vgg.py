@@ -35,6 +35,18 @@ class VGG16Scheme2Trunk(nn.Module):
             layer.fuse_pool = i + 1 < len(VGG16_CFG) and VGG16_CFG[i + 1] == "M"
             self.features.append(layer)
 
+    def set_normalization(self, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
+        """Per-channel mean / std (on the 0..1 scale, like timm's IMAGENET_DEFAULT_MEAN / STD) applied to uint8 inputs."""
+        self._norm = (tuple(float(m) * 255.0 for m in mean), tuple(1.0 / (float(s) * 255.0) for s in std))
+        self._norm_dev = {}            # device -> (mean255, inv_std255) fp32 tensors (plain attributes: .bfloat16() must not round them)
+
+    def _norm_tensors(self, device):
+        if not hasattr(self, "_norm"):
+            self.set_normalization()
+        if device not in self._norm_dev:
+            self._norm_dev[device] = tuple(torch.tensor(v, dtype=torch.float32, device=device) for v in self._norm)
+        return self._norm_dev[device]
+
     def conv_layers(self):
         return [m for m in self.features if isinstance(m, LowRankExpConvV2)]
 
@@ -45,6 +57,10 @@ class VGG16Scheme2Trunk(nn.Module):
         return x
 
     def forward(self, x):
-        """x: (B,3,H,W) logical NCHW, bf16 (fused tcgen05 path) or fp32 (exact FFMA path)."""
+        """x: (B,3,H,W) logical NCHW, bf16 (fused tcgen05 path) or fp32 (exact FFMA path) — or uint8 images as an image loader
+        holds them: normalised on the device, (x - 255 mean) / (255 std), in the same kernel that lays them out as bf16 NHWC."""
+        if x.dtype == torch.uint8:
+            mean255, inv_std255 = self._norm_tensors(x.device)
+            return B.from_nhwc(self.forward_nhwc(B.u8_to_nhwc_norm(x.contiguous(), mean255, inv_std255, 16)))
         c_pad = 16 if x.dtype == torch.bfloat16 else None
         return B.from_nhwc(self.forward_nhwc(B.to_nhwc(x, c_pad)))

@@ -55,6 +55,38 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_smallc_kernel(const TI* __re
     }
 }
 
+// uint8 images (what an image loader holds on the host: timm's prefetch loader ships uint8 NCHW batches to the GPU and normalises
+// there, `input.float().sub_(mean * 255).div_(std * 255)`) -> normalised bf16 NHWC zero-padded to CPAD channels, in one pass.
+// A thread owns 4 consecutive pixels: one 4-byte load per plane, CPAD * 8 bytes of stores.  HW % 4 == 0.
+template <int CPAD>
+__global__ void __launch_bounds__(256) u8_nchw_to_nhwc_norm_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                                   const float* __restrict__ mean255, const float* __restrict__ inv_std255,
+                                                                   int C, int HW, long long total4) {
+    float mu[8], is[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { mu[c] = c < C ? mean255[c] : 0.f; is[c] = c < C ? inv_std255[c] : 0.f; }
+    const int HW4 = HW >> 2;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total4; idx += (long long)gridDim.x * blockDim.x) {
+        const long long b = idx / HW4;
+        const int p4 = (int)(idx - b * HW4);
+        const uint8_t* s = src + (size_t)b * C * HW + (size_t)p4 * 4;
+        uint32_t plane[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) plane[c] = c < C ? __ldg(reinterpret_cast<const uint32_t*>(s + (size_t)c * HW)) : 0u;
+        __nv_bfloat16* d = dst + ((size_t)b * HW + (size_t)p4 * 4) * CPAD;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            alignas(16) __nv_bfloat16 v[CPAD];
+#pragma unroll
+            for (int c = 0; c < CPAD; ++c)
+                v[c] = (c < 8 && c < C) ? __float2bfloat16_rn(((float)((plane[c < 8 ? c : 0] >> (8 * q)) & 0xffu) - mu[c < 8 ? c : 0]) * is[c < 8 ? c : 0])
+                                        : __float2bfloat16_rn(0.f);
+#pragma unroll
+            for (int w = 0; w < CPAD / 8; ++w) reinterpret_cast<uint4*>(d + q * CPAD)[w] = *reinterpret_cast<const uint4*>(&v[8 * w]);
+        }
+    }
+}
+
 // src [B][HW][c_pad] -> dst [B][C][HW]
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const TI* __restrict__ src, TO* __restrict__ dst,
@@ -164,6 +196,21 @@ int cna_nchw_to_nhwc(const void* src, void* dst, int B, int C, int H, int W, int
     if (src_dtype == CNA_BF16 && dst_dtype == CNA_BF16) return launch_to_nhwc<__nv_bfloat16, __nv_bfloat16>(src, dst, B, C, H, W, c_pad, st);
     if (src_dtype == CNA_BF16 && dst_dtype == CNA_F32) return launch_to_nhwc<__nv_bfloat16, float>(src, dst, B, C, H, W, c_pad, st);
     CNA_FAIL("unsupported dtype pair");
+}
+
+int cna_u8_nchw_to_nhwc_norm(const void* src_u8, void* dst_bf16, const float* mean255, const float* inv_std255, int B, int C, int H,
+                             int W, int c_pad, void* stream) {
+    CNA_CHECK(src_u8 && dst_bf16 && mean255 && inv_std255 && B > 0 && H > 0 && W > 0, "bad arguments");
+    CNA_CHECK(C >= 1 && C <= 8 && (c_pad == 8 || c_pad == 16) && c_pad >= C, "1..8 image channels, padded to 8 or 16");
+    CNA_CHECK((H * W) % 4 == 0 && (reinterpret_cast<uintptr_t>(src_u8) & 3) == 0 && (reinterpret_cast<uintptr_t>(dst_bf16) & 15) == 0,
+              "H*W must be a multiple of 4 and the buffers 4- / 16-byte aligned");
+    const long long total4 = (long long)B * H * W / 4;
+    const int grid = (int)std::min<long long>(ceil_div_ll(total4, 256), 148LL * 16);
+    cudaStream_t st = as_stream(stream);
+    if (c_pad == 8) u8_nchw_to_nhwc_norm_kernel<8><<<grid, 256, 0, st>>>((const uint8_t*)src_u8, (__nv_bfloat16*)dst_bf16, mean255, inv_std255, C, H * W, total4);
+    else u8_nchw_to_nhwc_norm_kernel<16><<<grid, 256, 0, st>>>((const uint8_t*)src_u8, (__nv_bfloat16*)dst_bf16, mean255, inv_std255, C, H * W, total4);
+    CNA_LAUNCH_OK();
+    return 0;
 }
 
 int cna_nhwc_to_nchw(const void* src, void* dst, int B, int C, int H, int W, int c_pad,

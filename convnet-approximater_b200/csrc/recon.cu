@@ -59,11 +59,11 @@ __global__ void __launch_bounds__(256) l2_norm_backward_kernel(const T* __restri
                                                               const float* __restrict__ norms, const float* __restrict__ upstream,
                                                               T* __restrict__ g, long long per_sample) {
     const int b = blockIdx.y;
-    const float nrm = norms[b];
+    const float nrm = norms ? norms[b] : 1.f;
     const float f = nrm > 0.f ? upstream[b] / nrm : 0.f;
     const size_t off = (size_t)b * per_sample;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_sample; i += (long long)gridDim.x * blockDim.x)
-        g[off + i] = from_f32<T>((to_f32(ldg(yn + off + i)) - to_f32(ldg(yo + off + i))) * f);
+        g[off + i] = from_f32<T>((to_f32(ldg(yn + off + i)) - (yo ? to_f32(ldg(yo + off + i)) : 0.f)) * f);
 }
 
 // ---- bf16, 16-byte vectorised variants (per_sample % 8 == 0): the reconstruction step's loss kernels move 3 passes over y, so
@@ -326,7 +326,7 @@ int cna_l2_recon_loss_grad_bias_acc(const void* y_new, const void* y_old, float*
 
 int cna_l2_norm_backward(const void* y_new, const void* y_old, const float* norms, const float* upstream, void* grad, int B,
                          long long per_sample, int dtype, void* stream) {
-    CNA_CHECK(y_new && y_old && norms && upstream && grad, "null pointer");
+    CNA_CHECK(y_new && upstream && grad, "null pointer");          // y_old == NULL: zero; norms == NULL: one (plain per-sample scaling)
     CNA_CHECK(B > 0 && B <= 65535 && per_sample > 0, "bad dims");
     dim3 grid((unsigned)std::min<long long>(ceil_div_ll(per_sample, 256 * 8), 148 * 4), B);
     cudaStream_t st = as_stream(stream);

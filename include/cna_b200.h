@@ -40,6 +40,12 @@ unsigned long long cna_launch_count(void);
 /* src NCHW (src_dtype) -> dst NHWC with channel count c_pad >= C (extra channels zero-filled). */
 int cna_nchw_to_nhwc(const void* src, void* dst, int B, int C, int H, int W, int c_pad,
                      int src_dtype, int dst_dtype, void* stream);
+/* uint8 NCHW images -> normalised bf16 NHWC, channels zero-padded to c_pad (8 or 16):  dst = (src - mean255[c]) * inv_std255[c].
+ * This is the input boundary of an image pipeline: the reference's loaders (timm create_loader with its prefetcher,
+ * src/approx/hooks/fps.py:38-49, hooks/finetune.py:164-175) ship uint8 batches to the GPU and normalise there with
+ * mean * 255 / std * 255; here the normalisation is fused with the layout change, so a batch costs 1 byte per value over PCIe. */
+int cna_u8_nchw_to_nhwc_norm(const void* src_u8, void* dst_bf16, const float* mean255, const float* inv_std255, int B, int C, int H,
+                             int W, int c_pad, void* stream);
 /* src NHWC with c_pad channels -> dst NCHW with C channels. */
 int cna_nhwc_to_nchw(const void* src, void* dst, int B, int C, int H, int W, int c_pad,
                      int src_dtype, int dst_dtype, void* stream);
@@ -249,7 +255,8 @@ int cna_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* e
                        float beta2, float eps, float weight_decay, int* step_dev, float grad_scale, void* stream);
 
 /* Backward of the per-sample output-L2 norm for autograd callers (the loss hook get_l2_error, src/approx/hooks/finetune.py:80-82,
- * reached from total_loss.backward() at :329): grad[b] = (y_new[b] - y_old[b]) * upstream[b] / norms[b], 0 where the norm is 0. */
+ * reached from total_loss.backward() at :329): grad[b] = (y_new[b] - y_old[b]) * upstream[b] / norms[b], 0 where the norm is 0.
+ * y_old == NULL is read as zero and norms == NULL as one, i.e. grad[b] = y_new[b] * upstream[b] (scaling a saved unit gradient). */
 int cna_l2_norm_backward(const void* y_new, const void* y_old, const float* norms, const float* upstream, void* grad, int B,
                          long long per_sample, int dtype, void* stream);
 
@@ -293,6 +300,18 @@ int cna_recon_sync_step(void* const* peers_host, int rank, int world, long long 
                         const int* layer_dims_host, void* const* layer_ptrs_host, int nlayers, float lr, float beta1, float beta2,
                         float eps, float weight_decay, float grad_scale, void* stream);
 int cna_recon_sync_error(const void* local_buffer, int* err_host);
+
+/* Alternating fit of scheme-1 bases with a nuclear-norm penalty on the device — replaces the cvxpy loop of LowRankExpV1.optimize
+ * (src/approx/core/low_rank_exp.py:127-135, 160-176):
+ *     minimise  sum_r || W_r - A_r B ||_2 + lambda * sum_m || reshape(B_m, d, d) ||_*   over A = weights (R x M), B = bases (M x d*d),
+ * alternately in B (majorise-minimise + FISTA with singular-value soft-thresholding, `mm_rounds` x `fista_iters`) and in A (closed
+ * form W B^T (B B^T)^+), for every lambda of lmda_list_host in order (warm starts), at most max_iter alternations per lambda, stopping
+ * when the objective moves by less than epsilon — the reference's schedule.  weights / bases hold the initial point on entry (device,
+ * fp32) and the result on exit.  obj_trace_host (optional, capacity trace_cap) receives the objective after every B-step and A-step.
+ * W: R x d*d fp32 device; d <= 8; M <= 16.  Synchronises the stream (the stopping rule is evaluated on the host). */
+int cna_lowrank1_alt_fit(const float* W, int R, int d, int M, float* weights, float* bases, const double* lmda_list_host, int n_lmda,
+                         int max_iter, double epsilon, int mm_rounds, int fista_iters, double* obj_trace_host, int trace_cap,
+                         int* trace_len_host, void* stream);
 
 /* 2x2/stride-2 max pool, NHWC (VGG trunk glue between the approximated convs). */
 int cna_maxpool2x2(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream);

@@ -182,3 +182,24 @@ def test_host_pipeline_matches_direct_call(channels_last_out):
         for x, y in zip(xs, ys):
             ref = m(x.cuda()).cpu()
             assert torch.equal(ref, y)
+
+
+def test_uint8_image_input_is_normalised_in_the_layout_kernel():
+    """uint8 NCHW images (what the reference's timm loaders ship to the GPU, hooks/fps.py:38-49) through
+    cna_u8_nchw_to_nhwc_norm == the same images normalised with (x - 255 mean) / (255 std) in fp32 and rounded to bf16."""
+    from approx import backend as B
+    from approx.models import VGG16Scheme2Trunk
+    torch.manual_seed(1)
+    x = torch.randint(0, 256, (3, 3, 40, 36), dtype=torch.uint8)
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    mean255 = torch.tensor([m * 255.0 for m in mean]); inv = torch.tensor([1.0 / (s * 255.0) for s in std])
+    want = ((x.float() - mean255.view(1, 3, 1, 1)) * inv.view(1, 3, 1, 1)).bfloat16()
+    got = B.u8_to_nhwc_norm(x.cuda(), mean255.cuda(), inv.cuda(), 16)
+    assert got.shape == (3, 40, 36, 16)
+    assert torch.equal(got[..., :3].permute(0, 3, 1, 2).cpu(), want) and float(got[..., 3:].abs().max()) == 0.0
+    trunk = VGG16Scheme2Trunk(16).cuda().bfloat16().eval()
+    xi = torch.randint(0, 256, (2, 3, 32, 32), dtype=torch.uint8)
+    with torch.no_grad():
+        y_u8 = trunk(xi.cuda())
+        y_bf = trunk(((xi.float() - mean255.view(1, 3, 1, 1)) * inv.view(1, 3, 1, 1)).bfloat16().cuda())
+    assert torch.equal(y_u8, y_bf)

@@ -1,19 +1,16 @@
 #!/bin/bash
-mkdir -p gpurun_out/c8
-O=gpurun_out/c8
-# the fused conv kernel changed (second GEMM1 issuer, merged producer, per-copy A barriers): its own tests first, with a short per-test timeout
+mkdir -p gpurun_out/c9
+O=gpurun_out/c9
 timeout 150 python -m pytest tests/test_lowrank2_fused_gpu.py tests/test_baseline_sizes_gpu.py -q --timeout 60 -x -k "not msca and not alexnet" > $O/pytest_fused.log 2>&1
 rc=$?; echo "pytest rc=$rc" >> $O/pytest_fused.log
 if [ $rc -ne 0 ]; then echo "fused tests failed: skipping the rest" > $O/done; exit 0; fi
 timeout 1500 python -m pytest tests -m gpu -q --timeout 300 > $O/pytest.log 2>&1; echo "pytest rc=$?" >> $O/pytest.log
-# fused conv: second GEMM1 issuer A/B (default: on wherever warp 15 is free; =0 off everywhere; =1 also on the 64-channel layers)
-for g in default 0 1; do
+for g in default 1; do
   if [ $g = default ]; then unset CNA_LR2_G1B; else export CNA_LR2_G1B=$g; fi
   timeout 300 python bench.py --per-layer --steps 10 --no-msca --no-recon --no-lib --no-cpu > $O/bench_g1b_$g.json 2> $O/bench_g1b_$g.err
 done
 unset CNA_LR2_G1B
-for spec in "3 64 64 224 64" "64 64 64 224 64" "64 64 16 224 64"; do
-  set -- $spec
-  timeout 120 python benchmarks/trace_lowrank2.py --C $1 --N $2 --K $3 --H $4 --batch $5 --tiles 48 --quiet 1 > $O/trace_C$1_N$2_K$3_H$4.log 2>&1
-done
+timeout 300 python benchmarks/bench_dwconv.py --batch 256 > $O/dwconv_b256.log 2>&1
+timeout 600 python benchmarks/low_rank_exp_spr.py > $O/spr_bf16.log 2>&1
+timeout 600 python benchmarks/low_rank_exp_spr.py --decomp > $O/spr_bf16_decomp.log 2>&1
 echo done > $O/done

@@ -14,7 +14,8 @@ import torch
 
 F32, BF16 = 0, 1
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libcna_b200.so")
+# CNA_B200_LIB: load another build of the same library (A/B measurements of a kernel revision on one box)
+LIB_PATH = os.environ.get("CNA_B200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libcna_b200.so")
 
 _lib = None
 
@@ -284,24 +285,48 @@ def lowrank1_fused_supported(B, H, W, C, N, M, d, separable) -> bool:
     return bool(lib().cna_lowrank1_fused_supported(int(B), int(H), int(W), int(C), int(N), int(M), int(d), int(bool(separable))))
 
 
-def lowrank1_pack_s(s_conv, M: int) -> torch.Tensor:
+def _pad_bases(w: torch.Tensor, C: int, M: int, m_pad: int) -> torch.Tensor:
+    """(C*M, ...) per-wide-channel tensor -> (C*m_pad, ...) with zeros for the padding bases m >= M of every input channel."""
+    if m_pad == M:
+        return w
+    out = torch.zeros((C, m_pad) + tuple(w.shape[1:]), device=w.device, dtype=w.dtype)
+    out[:, :M] = w.reshape((C, M) + tuple(w.shape[1:]))
+    return out.reshape((C * m_pad,) + tuple(w.shape[1:]))
+
+
+def lowrank1_pack_s(s_conv, M: int, m_pad: int | None = None) -> torch.Tensor:
     """Basis filters of LowRankExpConvV1.s_conv in the per-chunk layout the fused scheme-1 kernel stages with one bulk copy:
-    fp32 [C*M/64][rows][64] with rows = d*d taps + bias (grouped d x d conv) or d v-taps + d h-taps (SeparableConv).  Values
-    are rounded through bf16 like every other bf16-path weight."""
+    fp32 [C*m_pad/64][rows][64] with rows = d*d taps + bias (grouped d x d conv) or d v-taps + d h-taps (SeparableConv).  Values
+    are rounded through bf16 like every other bf16-path weight.  m_pad > M pads every input channel's bases with zero filters, so
+    a layer with M in 2..7 bases runs on the kernel instance for 4 or 8 (the padding channels produce zeros and meet zero weights)."""
+    m_pad = M if m_pad is None else m_pad
     r = lambda w: w.detach().to(torch.bfloat16).to(torch.float32)
     if hasattr(s_conv, "v_conv"):
         v, h = s_conv.v_conv.weight, s_conv.h_conv.weight
-        CM, d = v.shape[0], v.shape[2]
-        rows = torch.cat([r(v).reshape(CM // 64, 64, d), r(h).reshape(CM // 64, 64, d)], 2)
+        C, d = v.shape[0] // M, v.shape[2]
+        CM = C * m_pad
+        v, h = _pad_bases(r(v), C, M, m_pad), _pad_bases(r(h), C, M, m_pad)
+        rows = torch.cat([v.reshape(CM // 64, 64, d), h.reshape(CM // 64, 64, d)], 2)
     else:
         w = s_conv.weight
-        CM, d = w.shape[0], w.shape[2]
-        b = s_conv.bias.detach().to(torch.float32) if s_conv.bias is not None else torch.zeros(CM, device=w.device)
-        rows = torch.cat([r(w).reshape(CM // 64, 64, d * d), b.reshape(CM // 64, 64, 1)], 2)
+        C, d = w.shape[0] // M, w.shape[2]
+        CM = C * m_pad
+        b = s_conv.bias.detach().to(torch.float32) if s_conv.bias is not None else torch.zeros(C * M, device=w.device)
+        w, b = _pad_bases(r(w), C, M, m_pad), _pad_bases(b, C, M, m_pad)
+        rows = torch.cat([w.reshape(CM // 64, 64, d * d), b.reshape(CM // 64, 64, 1)], 2)
     rows = rows.transpose(1, 2)                                             # [chunk][row][64 wide channels]
     # within a row: unit u's channels 8u..8u+3 at floats [4u, 4u+4), channels 8u+4..8u+7 at [32+4u, 32+4u+4): a quarter-warp's
     # 16-byte loads cover 128 contiguous bytes
     return rows.reshape(rows.shape[0], rows.shape[1], 8, 2, 4).transpose(2, 3).reshape(rows.shape[0], rows.shape[1], 64).contiguous()
+
+
+def lowrank1_pack_d(d_conv_weight: torch.Tensor, C: int, M: int, m_pad: int) -> torch.Tensor:
+    """d_conv.weight (N, C*M, 1, 1) -> bf16 [N][C*m_pad] with zero columns for the padding bases."""
+    N = d_conv_weight.shape[0]
+    w = d_conv_weight.detach().reshape(N, C * M)
+    if m_pad != M:
+        w = _pad_bases(w.t().contiguous(), C, M, m_pad).t().contiguous()
+    return conv1x1_pack(w.reshape(N, C * m_pad, 1, 1))
 
 
 def lowrank1_fused(x, s_packed, dw_packed, d_bias, M: int, d: int, separable: bool):

@@ -73,6 +73,9 @@ def l2_norm(y_new, y_old):
 
 
 def cache_module_output(module, inputs, output):
+    # NOT cloned, exactly like the reference (hooks/finetune.py:76-77): when the next module works in place — nn.ReLU(inplace=True)
+    # after every conv of the reference's AlexNet — the cached teacher target is what that module leaves behind (relu(y_old)), and
+    # the student layers are fitted to THAT.  Kept for result parity with the reference's fine-tuning runs.
     module.cache['ori_output'] = output
 
 

@@ -64,17 +64,22 @@ class LowRankExpConvV1(nn.Module):
         return self.d_conv.bias
 
     def _fused(self, x):
-        """One tcgen05 kernel for d_conv(s_conv(x)) (csrc/lowrank1_tc.cu) when the layer fits it: bf16, stride 1, 'same'."""
+        """One tcgen05 kernel for d_conv(s_conv(x)) (csrc/lowrank1_tc.cu) when the layer fits it: bf16, stride 1, 'same'.  The kernel
+        has instances for 4 and 8 bases per input channel; any other num_base <= 8 is padded up with zero bases (the reference's own
+        sweep, scripts/low_rank_exp_spr.py:35-63, walks num_base = 2..11)."""
         d = self.kernel_size[0]
+        M = self.num_base
         sep = isinstance(self.s_conv, SeparableConv)
-        if not (x.dtype == torch.bfloat16 and x.is_contiguous() and self.kernel_size == (d, d) and self.stride == (1, 1)
-                and self.padding == (d // 2, d // 2) and (self.in_channels * self.num_base) % 64 == 0
-                and B.lowrank1_fused_supported(*x.shape[:3], self.in_channels, self.out_channels, self.num_base, d, sep)):
+        m_pad = 4 if M <= 4 else (8 if M <= 8 else 0)
+        if not (m_pad and x.dtype == torch.bfloat16 and x.is_contiguous() and self.kernel_size == (d, d) and self.stride == (1, 1)
+                and self.padding == (d // 2, d // 2) and (self.in_channels * m_pad) % 64 == 0
+                and B.lowrank1_fused_supported(*x.shape[:3], self.in_channels, self.out_channels, m_pad, d, sep)):
             return None
         params = tuple(self.s_conv.parameters())
-        sp = _ops.cached(self, "s_packed", params, torch.bfloat16, lambda: B.lowrank1_pack_s(self.s_conv, self.num_base))
-        dp = _ops.cached(self.d_conv, "w_1x1_tc", (self.d_conv.weight,), torch.bfloat16, lambda: B.conv1x1_pack(self.d_conv.weight))
-        return B.lowrank1_fused(x, sp, dp, _ops.bias_f32(self.d_conv), self.num_base, d, sep)
+        sp = _ops.cached(self, "s_packed", params, torch.bfloat16, lambda: B.lowrank1_pack_s(self.s_conv, M, m_pad))
+        dp = _ops.cached(self.d_conv, "w_1x1_tc_pad", (self.d_conv.weight,), torch.bfloat16,
+                         lambda: B.lowrank1_pack_d(self.d_conv.weight, self.in_channels, M, m_pad))
+        return B.lowrank1_fused(x, sp, dp, _ops.bias_f32(self.d_conv), m_pad, d, sep)
 
     def forward_nhwc(self, x, fused=True):
         if fused:

@@ -175,7 +175,12 @@ dw_tile_kernel(const T* __restrict__ x, const T* __restrict__ w /*[KH*KW][C]*/, 
 // from global memory; neighbouring runs' halo re-reads hit L1/L2) and its 4 x K weights in registers:
 // ~11 (K = 7) to ~28 (K = 21) instructions per element.  Lanes run over channel groups, then pixels, so loads coalesce.
 // ------------------------------------------------------------------------------------------------
-template <int K> struct StripRun { static constexpr int value = K <= 7 ? 16 : 8; };   // outputs per thread along the strip axis
+// Outputs per thread along the strip axis and resident CTAs per SM.  The strips are HBM-bound, so what matters is how many loads are in
+// flight per SM, i.e. OCCUPANCY: with 16-output runs the K = 7 kernel needed 170-210 registers — one 8-warp CTA per SM, whose load
+// phases and FMA phases never overlapped (43 % of the HBM peak by ncu DRAM bytes, profiles/r02_dwconv_b256_ncu_summary.csv).
+// 8-output runs fit 2 CTAs per SM for every K without spilling (3 CTAs for K = 7 spill ~84 bytes per thread).
+template <int K> struct StripRun { static constexpr int value = 8; };
+template <int K> struct StripCtas { static constexpr int value = 2; };
 
 
 template <typename T> struct Vec4;
@@ -201,7 +206,7 @@ template <> struct Vec4<float> {
 };
 
 template <typename T, int K, bool ALONG_W, bool EXTRAS>
-__global__ void __launch_bounds__(256, K >= 21 ? 2 : 1)
+__global__ void __launch_bounds__(256, StripCtas<K>::value)
 dw_strip_kernel(const T* __restrict__ x, const T* __restrict__ w /*[K][C]*/, const float* __restrict__ bias,
                 const float* __restrict__ res, int res_p, const T* __restrict__ add, T* __restrict__ y,
                 int B, int H, int W, int C, long long nitems) {

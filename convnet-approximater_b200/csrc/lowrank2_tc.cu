@@ -32,6 +32,13 @@
 // TMEM (512 columns): T accumulators 2 x 64 | A copies NABUF x 3 x KP/2 | Y accumulators 2 x NT2, with
 // NABUF = 2 for NT2 = 64 and 1 for NT2 = 128 (TMEM is full there; GEMM1 of the next tiles fills the tensor pipe
 // while the single A buffer is rewritten).
+//
+// Round-2 experiments that were measured and NOT kept (same box, same run: profiles/r02_fused_conv_experiments.txt):
+//   * a second GEMM1 issuer on the otherwise idle warp (even / odd tiles on the two T accumulators; needs a progress hand-shake
+//     between the issuers, because an mbarrier can only be waited on one phase ahead) + one TMA producer warp polling both
+//     rings: layers 3-4 gain 4 %, layer 2 loses 13 %, the streamed layers 4-7 % — trunk 2.90 -> 3.00 ms;
+//   * handing the three bf16 copies of T to GEMM2 one by one (own full/empty barrier pair per copy): layer 2 0.68 -> 0.77 ms — issuer
+//     and epilogue then wait for each other three times per tile instead of once.
 #include "common.cuh"
 #include "ptx.cuh"
 

@@ -123,3 +123,24 @@ def test_random_shapes_agree_with_unfused_path():
         err = float((y.float() - y2.float()).norm() / y2.float().norm())
         assert err < 1e-3, (Bn, C, N, d, M, H, W, sep, err)
         done += 1
+
+
+@pytest.mark.parametrize("sep", [False, True])
+@pytest.mark.parametrize("M", [2, 3, 5, 6, 7])
+def test_num_base_outside_4_and_8_runs_fused_by_padding(M, sep):
+    """The reference's own sweep (scripts/low_rank_exp_spr.py:35-63) walks num_base = 2..11: every M <= 8 stays on the fused kernel
+    (padded with zero bases to the 4- or 8-basis instance) and still matches the bf16 oracle."""
+    from approx import backend as B
+    C, N, d, H = 64, 96, 3, 13
+    m = build(C, N, d, M, sep, 11 + M)
+    x = torch.randn(4, C, H, H, generator=torch.Generator().manual_seed(2)).bfloat16()
+    with torch.no_grad():
+        ref = oracle(m, x, sep).float()
+    mg = m.cuda().eval()
+    xn = B.to_nhwc(x.cuda())
+    with torch.no_grad():
+        mg.forward_nhwc(xn)                          # first call packs
+        before = B.launch_count()
+        y = mg.forward_nhwc(xn)
+        assert B.launch_count() - before == 1, "expected exactly the fused kernel"
+    assert O.compare4d(ref, y.permute(0, 3, 1, 2).float().cpu()) < 1e-3

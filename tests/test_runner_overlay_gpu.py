@@ -189,6 +189,7 @@ def test_l2_reconstruct_hook_follows_the_reference_arithmetic(mode, tmp_path):
     _run(script, [cfg, work, "l2", mode], overlay=True)
     got = torch.load(os.path.join(work, "out.pth"))
     P = {k: v.clone().float().requires_grad_(True) for k, v in torch.load(os.path.join(work, "before.pth"))["student"].items()}
+    P0 = {k: v.detach().clone() for k, v in P.items()}
     SUBS = [(3, 64, 5), (6, 192, 3), (8, 384, 3), (10, 256, 3)]
 
     def forward(x, use_new, cache, norms):
@@ -200,7 +201,9 @@ def test_l2_reconstruct_hook_follows_the_reference_arithmetic(mode, tmp_path):
                 norms.append(O.l2_recon_norm(y, cache[i]))
             else:
                 y = F.conv2d(x, P[pre + ".old.weight"], P[pre + ".old.bias"], 1, d // 2)
-                cache[i] = y.detach()
+                # the reference caches the teacher layer's output tensor ITSELF (hooks/finetune.py:76-77, no clone) and AlexNet's next
+                # module is nn.ReLU(inplace=True): by the time the student's norm is taken the cached target holds relu(y_old)
+                cache[i] = torch.relu(y).detach()
             return y
         x = F.max_pool2d(F.relu(F.conv2d(x, P["features.0.weight"], P["features.0.bias"], 4, 2)), 3, 2)
         x = F.max_pool2d(F.relu(sub(3, x, 64, 5)), 3, 2)
@@ -252,6 +255,12 @@ def test_l2_reconstruct_hook_follows_the_reference_arithmetic(mode, tmp_path):
     assert len(hist) == len(losses) == 6
     for a, b in zip(hist, losses):
         assert abs(a - b) / abs(b) < 2e-3, (hist, losses)
+    # Adam moves every trained element by ~lr per step whatever the gradient's size, so fp32 noise in near-zero gradients shows up
+    # at the scale of the UPDATE, not of the parameter: the two trajectories must agree to a small fraction of the distance moved
+    moved = 0
     for k, v in P.items():
         ref, mine = v.detach(), got["after"][k].float()
-        assert (ref - mine).norm() <= 2e-3 * ref.norm() + 1e-6, k
+        step = (ref - P0[k]).norm()
+        moved += int(step > 0)
+        assert (ref - mine).norm() <= 0.1 * step + 1e-5 * (1 + ref.norm()), (k, (ref - mine).norm().item(), step.item())
+    assert moved >= 20

@@ -453,7 +453,7 @@ def run_ours(args):
         msca_rec["n_gpus"] = world
         msca_rec["scaling"] = "weak (batch 32 per GPU, no collective)"
     if not args.no_recon:
-        recon_rec = bench_recon(dev, world, rank, None, K, global_batch=256, steps=max(3, min(args.steps, 10)))
+        recon_rec = bench_recon(dev, world, rank, None, K, global_batch=args.recon_batch, steps=max(3, min(args.steps, 10)))
     if rank == 0:
         peaks = {}
         try:
@@ -558,6 +558,7 @@ def main():
     ap.add_argument("--no-msca", action="store_true", help="skip the MSCA (config 4) sub-record")
     ap.add_argument("--no-recon", action="store_true", help="skip the reconstruction (config 3) sub-record")
     ap.add_argument("--no-lib", action="store_true", help="skip the torch/cuDNN library baseline of the trunk")
+    ap.add_argument("--recon-batch", type=int, default=256, help="GLOBAL batch of the reconstruction sub-record (BASELINE config 3: 256)")
     ap.add_argument("--per-layer", action="store_true", help="print per-layer time / GB/s to stderr")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

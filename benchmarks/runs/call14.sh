@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out/c14
+O=gpurun_out/c14
+timeout 600 python -m pytest tests/test_recon_gpu.py -q --timeout 120 > $O/pytest_recon.log 2>&1; echo "rc=$?" >> $O/pytest_recon.log
+timeout 300 python bench.py --steps 10 --no-msca --no-lib --no-cpu --recon-batch 32 > $O/bench_b32.json 2> $O/bench_b32.err
+timeout 300 python bench.py --steps 10 --no-msca --no-lib --no-cpu > $O/bench_b256.json 2> $O/bench_b256.err
+echo done > $O/done

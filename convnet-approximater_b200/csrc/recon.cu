@@ -270,7 +270,9 @@ static int l2_recon_impl(const void* y_new, const void* y_old, float* sumsq_scra
     if (dtype == CNA_BF16 && per_sample % 8 == 0 && aligned) {
         const long long ps8 = per_sample / 8;
         // ~8 CTAs per SM in total: enough to stream at full rate, few enough that the per-CTA bias atomics stay cheap
-        int slabs = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(ceil_div_ll(ps8, 256), 64), ceil_div_ll(148 * 8, B)));
+        // and at least 8 vectors per thread, so the per-CTA reduction atomics (N per CTA for the bias gradient, one per CTA for the
+        // sum of squares) do not outweigh the streaming on small per-sample sizes
+        int slabs = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(ceil_div_ll(ps8, 256 * 8), 64), ceil_div_ll(148 * 8, B)));
         const int N8 = N / 8;
         // bias-gradient fusion: every thread must keep the same 8 channels across its grid-stride iterations
         bool fuse_db = dbias != nullptr && N % 8 == 0 && N8 <= 2048;

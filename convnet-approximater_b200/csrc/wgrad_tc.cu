@@ -21,6 +21,7 @@
 #include "ptx.cuh"
 
 #include <cuda.h>
+#include <cmath>
 #include <mutex>
 
 namespace cna {
@@ -41,6 +42,7 @@ struct WgParams {
     long long s_a, s_k;     // output strides (in floats) of the A-channel and Bm-channel index
     int flip;               // tap index written: flip ? 1 - s : 1 + s
     uint32_t a_stage;       // bytes of one A stage (nsub sub-blocks)
+    int vec4;               // output rows are contiguous per lane and 16-byte aligned: use vector reductions in the epilogue
 };
 
 __host__ __device__ constexpr uint64_t wg_desc_hi(uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -127,6 +129,33 @@ wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         tc_fence_after_sync();
         for (int blk = 0; blk < nblk; ++blk) {
             const int a = (grp * p.nsub + blk * 2) * 64 + lg * 32 + lane;      // A channel of this lane
+            if (p.vec4) {
+                // h_conv layout dw[n][k][tap]: a lane's 64 x 3 results are ONE contiguous 768-byte row -> 16-byte vector reductions
+                // (red.global.add.v4.f32), a quarter of the scalar atomics.  Output element k*3 + tap comes from accumulator t = 2 - tap.
+                for (int c16 = 0; c16 < 4; ++c16) {
+                    uint32_t v0[16], v1[16], v2[16];
+                    tmem_ld16(tmem + (uint32_t)(blk * 3 + 0) * 64 + lane_addr + c16 * 16, v0);
+                    tmem_ld16(tmem + (uint32_t)(blk * 3 + 1) * 64 + lane_addr + c16 * 16, v1);
+                    tmem_ld16(tmem + (uint32_t)(blk * 3 + 2) * 64 + lane_addr + c16 * 16, v2);
+                    tmem_ld_wait();
+                    if (a < p.Ca) {
+                        float* row = out + (long long)a * 192 + c16 * 48;
+                        float e[48];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            e[i * 3 + 0] = __uint_as_float(v2[i]);      // tap 0 <- accumulator 2
+                            e[i * 3 + 1] = __uint_as_float(v1[i]);
+                            e[i * 3 + 2] = __uint_as_float(v0[i]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 12; ++j)
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + 4 * j), "f"(e[4 * j]), "f"(e[4 * j + 1]),
+                                         "f"(e[4 * j + 2]), "f"(e[4 * j + 3])
+                                         : "memory");
+                    }
+                }
+                continue;
+            }
 #pragma unroll
             for (int t = 0; t < 3; ++t) {
                 const int tap = p.flip ? 2 - t : t;                             // s = t - 1; flip: 1 - s
@@ -218,13 +247,22 @@ static int wgrad3_impl(const void* a, const void* bm, float* dw, int B, int H, i
     } else {                    // h_conv: dw[n][k][t] = D_{1-t}[n][k]  -> (N, K, 1, 3)
         p.s_a = (long long)kb * 3; p.s_k = 3; p.flip = 1;
     }
+    p.vec4 = (!wide_is_input && kb == 64 && (reinterpret_cast<uintptr_t>(dw) & 15) == 0) ? 1 : 0;
     const size_t smem = (size_t)kWgStages * (p.a_stage + kWgBTile) + 1024 + 1024;
     CNA_CHECK(smem <= (size_t)max_smem, "shared-memory plan does not fit");
     CUtensorMap tm_a, tm_b;
     if (wg_encode(&tm_a, a, ca_stride, B, H, W, axis, 10)) return 1;
     if (wg_encode(&tm_b, bm, kb_stride, B, H, W, axis, 8)) return 1;
     if (zero_first) CNA_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Ca * kb * 3, as_stream(stream)));
-    dim3 grid((unsigned)std::min(p.ntiles, std::max(1, num_sms / p.groups)), (unsigned)p.groups);
+    // CTAs per channel group.  Every CTA ends with the split-K reduction of its accumulators — nsub/2 x 3 taps x 64 columns x 128
+    // lanes fp32 atomics (49 152 per 256-channel group) whatever the number of tiles it summed — so with few tiles (small per-GPU
+    // batches: the 8-GPU reconstruction step runs 32 images per rank) the epilogue, not the MMAs, sets the kernel's time
+    // (88 us for a 512-channel layer at 28 x 28 x 32 images, 5x the batch-256 time / 8).  Balance the two terms:
+    // T(g) ~ ntiles / g * t_tile + g * groups * atomics / rate, t_tile ~ 1 us, rate ~ 83 atomics/ns  ->  g* = sqrt(1.7 ntiles / groups).
+    const int g_cap = std::max(1, num_sms / p.groups);
+    int gx = (int)std::lround(std::sqrt(1.7 * (double)p.ntiles / p.groups));
+    gx = std::max(1, std::min(gx, std::min(p.ntiles, g_cap)));
+    dim3 grid((unsigned)gx, (unsigned)p.groups);
     wgrad3_tc_kernel<<<grid, kWgThreads, smem, as_stream(stream)>>>(tm_a, tm_b, dw, p);
     CNA_LAUNCH_OK();
     return 0;

@@ -178,7 +178,10 @@ dw_tile_kernel(const T* __restrict__ x, const T* __restrict__ w /*[KH*KW][C]*/, 
 // Outputs per thread along the strip axis and resident CTAs per SM.  The strips are HBM-bound, so what matters is how many loads are in
 // flight per SM, i.e. OCCUPANCY: with 16-output runs the K = 7 kernel needed 170-210 registers — one 8-warp CTA per SM, whose load
 // phases and FMA phases never overlapped (43 % of the HBM peak by ncu DRAM bytes, profiles/r02_dwconv_b256_ncu_summary.csv).
-// 8-output runs fit 2 CTAs per SM for every K without spilling (3 CTAs for K = 7 spill ~84 bytes per thread).
+// 8-output runs fit 2 CTAs = 16 warps per SM without spilling: 1x7 / 7x1 0.51, 1x11 / 11x1 0.45 of the HBM peak at B = 256
+// (4-output runs at 3 CTAs per SM were measured too: 0.47 / 0.42 — more loads per output than the extra warps hide).  ncu on the
+// 1x7 kernel: long-scoreboard stalls dominate (3.9 per issue), 43 % issue-active: the next step for these is a TMA-fed shared-memory
+// pipeline, not more tuning of this register-window form.
 template <int K> struct StripRun { static constexpr int value = 8; };
 template <int K> struct StripCtas { static constexpr int value = 2; };
 

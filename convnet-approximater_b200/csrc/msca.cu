@@ -373,6 +373,10 @@ namespace cna {
 int msca_sd16_launch(const void* x, void* y, const float* w0, const float* b0, const float* w1cat, const float* b1cat,
                      const float* w2cat, const float* b2cat, const float* res, int res_p, const int* ks_host, int nb, int identity,
                      int B, int H, int W, int C, int dtype, cudaStream_t st);
+// msca_mma.cu: the same chain on mma.sync (bf16 only; -1 = configuration not covered)
+int msca_sdm_launch(const void* x, void* y, const float* w0, const float* b0, const float* w1cat, const float* b1cat,
+                    const float* w2cat, const float* b2cat, const float* res, int res_p, const int* ks_host, int nb, int identity,
+                    int B, int H, int W, int C, int dtype, cudaStream_t st);
 }
 
 using namespace cna;
@@ -397,7 +401,14 @@ int cna_msca_sd_forward(const void* x, void* y, const float* w0, const float* b0
     CNA_CHECK(res == nullptr || res_p > 0, "res without res_p");
     CNA_CHECK(B <= 65535, "batch too large for grid.y");
     {
-        static const bool old_only = [] { const char* e = getenv("CNA_MSCA_SD"); return e && e[0] == 'o'; }();   // diagnostic A/B switch
+        // diagnostic A/B switch: CNA_MSCA_SD=o -> the first-generation kernel below, =f -> the FFMA2 16-row march, default -> tensor path
+        static const char mode = [] { const char* e = getenv("CNA_MSCA_SD"); return e ? e[0] : 'm'; }();
+        const bool old_only = mode == 'o';
+        if (!old_only && mode != 'f') {
+            const int rc = msca_sdm_launch(x, y, w0, b0, w1cat, b1cat, w2cat, b2cat, res, res_p, ks_host, nb, identity, B, H, W, C, dtype,
+                                           as_stream(stream));
+            if (rc >= 0) return rc;
+        }
         if (!old_only) {
             const int rc = msca_sd16_launch(x, y, w0, b0, w1cat, b1cat, w2cat, b2cat, res, res_p, ks_host, nb, identity, B, H, W, C, dtype,
                                             as_stream(stream));

@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out/c24
+O=gpurun_out/c24
+timeout 240 python -m pytest tests/test_modules_gpu.py tests/test_baseline_sizes_gpu.py -m gpu -q --timeout 100 -x -k "msca or mscan" > $O/pytest_msca.log 2>&1; echo "pytest rc=$?" >> $O/pytest_msca.log
+timeout 200 python benchmarks/bench_msca.py > $O/msca_ws.log 2>&1; echo "rc=$?" >> $O/msca_ws.log
+CNA_MSCA_CPW=2 timeout 200 python benchmarks/bench_msca.py > $O/msca_cpw2.log 2>&1
+timeout 300 ncu --set full --import-source on --clock-control none -k regex:msca_sdw -s 3 -c 1 -o $O/msca_sdw python benchmarks/bench_msca.py --iters 1 > $O/ncu_full.log 2>&1
+echo done > $O/done

@@ -71,8 +71,8 @@ def conv0_sd_forward(msca, x):
         return None
     if mode == "chain" and B.msca_chain_supported(msca.num_channel, 5, ks, x.dtype):
         # CNA_MSCA_FUSED=chain: the register-tiled 5x5 + strip kernels enqueued back to back by one C call (three HBM round trips per
-        # cascade).  Measured on B200 at batch 32 over MSCAN-T's 13 blocks (profiles/r02_msca_block.txt): the one-pass 16-row-march
-        # kernel below wins for every form — original 1.75 vs 2.76 ms, MscaRep d1+fix 1.34 vs 1.64 ms — so it is the default.
+        # cascade).  Measured on B200 at batch 32 over MSCAN-T's 13 blocks (profiles/r02_msca_mma.txt): the one-pass marching
+        # kernel below wins for every form — original 0.98 vs 2.76 ms, MscaRep d1+fix 1.02 vs 1.64 ms — so it is the default.
         dw_w = lambda conv: _ops.cached(conv, "dw_w", (conv.weight,), x.dtype, lambda: B.pack_dw(conv.weight, x.dtype))
         return B.msca_chain(x.contiguous(), dw_w(conv0), _ops.bias_f32(conv0),
                             [dw_w(c.conv1) for c in cas], [_ops.bias_f32(c.conv1) for c in cas],

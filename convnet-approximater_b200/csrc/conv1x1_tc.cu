@@ -131,6 +131,22 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         const uint32_t lane_addr = (uint32_t)(lg * 32) << 16;
         const int m = lg * 32 + lane;
         const float lo = p.relu ? 0.f : -INFINITY;
+        // gate rows are fetched one 32-column chunk AHEAD (next chunk of this tile, or the first chunk of the warp's next tile):
+        // with four epilogue warps per SM the global-load latency of a chunk would otherwise be exposed once per tile
+        uint4 gq[4], gnext[4];
+        auto gate_fetch = [&](int it, int n0, uint4 (&dst)[4]) {
+            const long long r = (long long)(first + it * step) * 128 + m;
+            if (gate && it < my_tiles && r < p.P) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (n0 + q * 8 < p.N) {      // volatile: the load is issued HERE, not sunk down to its first use
+                        asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                     : "=r"(dst[q].x), "=r"(dst[q].y), "=r"(dst[q].z), "=r"(dst[q].w)
+                                     : "l"(reinterpret_cast<const uint4*>(gate + r * p.N + n0) + q));
+                    }
+            }
+        };
+        gate_fetch(0, 0, gnext);
         for (int it = 0; it < my_tiles; ++it) {
             const int buf = it & 1;
             const long long row = (long long)(first + it * step) * 128 + m;
@@ -141,11 +157,10 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             __nv_bfloat16* yrow = y + row * p.N;
             for (int n0 = 0; n0 < p.N; n0 += 32) {
                 uint32_t v[32];
-                uint4 gq[4];
-                if (grow && ok) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) gq[q] = __ldg(reinterpret_cast<const uint4*>(grow + n0) + q);
-                }
+                for (int q = 0; q < 4; ++q) gq[q] = gnext[q];
+                if (n0 + 32 < p.N) gate_fetch(it, n0 + 32, gnext);
+                else gate_fetch(it + 1, 0, gnext);
                 if (n0 + 32 <= p.N) {
                     tmem_ld32(tmem + buf * 256 + lane_addr + n0, v);
                 } else {   // N % 32 == 16

@@ -150,6 +150,7 @@ def bench_msca(dev, peaks, batch=32, iters=10):
     fully fused block; the two-kernel structure shipped moves 10) and the depthwise MACs against the FP32 pipe (the pipe the
     reference's depthwise convs run on; the bf16 original / rank-r forms now run them on mma.sync, csrc/msca_mma.cu)."""
     import contextlib
+    import copy
     import io
     from approx import backend as B
     from approx.core import MscaRep
@@ -171,10 +172,10 @@ def bench_msca(dev, peaks, batch=32, iters=10):
         elems_all += elems * nblk
         row = {"C": C, "H": H, "blocks": nblk}
         for name, cfg in forms.items():
-            m = src
+            m = copy.deepcopy(src)                         # .to() moves a module in place: every form gets its own copy
             if cfg is not None:
                 app = MscaRep(decomp=cfg[0], fix=cfg[1])
-                sub = app.initialize(src.cpu().float())
+                sub = app.initialize(copy.deepcopy(src))
                 with contextlib.redirect_stdout(io.StringIO()):
                     app.optimize(sub)
                 m = app.postprocess(sub)

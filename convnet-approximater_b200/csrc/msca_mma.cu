@@ -74,6 +74,7 @@ template <int K0, int K1, int K2> struct Lay {
 struct SdmParams {
     int B, H, W, C;
     int identity, res_p, strips, steps;
+    int lag;          // rows the output block trails the conv0 block: 10 (the widest strip's halo), or 0 when the whole image is one step
 };
 
 __device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t addr) {
@@ -211,7 +212,7 @@ __device__ __forceinline__ void sdm_vbranch(const uint32_t (&va)[3], const unsig
 
 // per-step ldmatrix / store offsets of one branch's T ring (shared by the warp's channels: a channel adds its plane offset)
 template <int K>
-__device__ __forceinline__ void sdm_ring_addrs(int base, int lane, int g, int t, uint32_t& st0, uint32_t& st1, uint32_t (&va)[3]) {
+__device__ __forceinline__ void sdm_ring_addrs(int base, int lag, int lane, int g, int t, uint32_t& st0, uint32_t& st1, uint32_t (&va)[3]) {
     using C = Br<K>;
     constexpr int P = K / 2;
     const int s0 = ring_slot<C::RING>(base, g), s1 = ring_slot<C::RING>(base, g + 8);
@@ -222,7 +223,7 @@ __device__ __forceinline__ void sdm_ring_addrs(int base, int lane, int g, int t,
     for (int i = 0; i < 3; ++i) {
         if (i <= C::NM) {
             const int blk = 2 * i + (i < C::NM ? (lane >> 4) : 0);
-            const int slot = ring_slot<C::RING>(base, -M_P - P + 8 * blk + (lane & 7));
+            const int slot = ring_slot<C::RING>(base, -lag - P + 8 * blk + (lane & 7));
             va[i] = slot * M_TPITCH + ((cbit ^ ((slot >> 1) & 3)) << 4);
         } else {
             va[i] = 0;
@@ -418,9 +419,9 @@ msca_sdm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
 
         // per-step ring addresses (shared by the warp's channels)
         uint32_t st0[3] = {0, 0, 0}, st1[3] = {0, 0, 0}, va[3][3];
-        if constexpr (K0 > 0) sdm_ring_addrs<K0>(Br<K0>::RING == 32 ? base32 : base40, lane, g, t, st0[0], st1[0], va[0]);
-        if constexpr (K1 > 0) sdm_ring_addrs<K1>(Br<K1>::RING == 32 ? base32 : base40, lane, g, t, st0[1], st1[1], va[1]);
-        if constexpr (K2 > 0) sdm_ring_addrs<K2>(Br<K2>::RING == 32 ? base32 : base40, lane, g, t, st0[2], st1[2], va[2]);
+        if constexpr (K0 > 0) sdm_ring_addrs<K0>(Br<K0>::RING == 32 ? base32 : base40, p.lag, lane, g, t, st0[0], st1[0], va[0]);
+        if constexpr (K1 > 0) sdm_ring_addrs<K1>(Br<K1>::RING == 32 ? base32 : base40, p.lag, lane, g, t, st0[1], st1[1], va[1]);
+        if constexpr (K2 > 0) sdm_ring_addrs<K2>(Br<K2>::RING == 32 ? base32 : base40, p.lag, lane, g, t, st0[2], st1[2], va[2]);
         const bool rin0 = 16 * s + g < H, rin1 = 16 * s + g + 8 < H;
 
         // ================= hpass: a0 block -> T_k rows [16s, 16s+16) of every branch =================
@@ -444,8 +445,8 @@ msca_sdm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
             uint32_t idoff[2][2];
 #pragma unroll
             for (int np = 0; np < 2; ++np) {
-                idoff[np][0] = ((base32 - M_P + 8 * np + 2 * t) & 31) * M_APITCH;
-                idoff[np][1] = ((base32 - M_P + 8 * np + 2 * t + 1) & 31) * M_APITCH;
+                idoff[np][0] = ((base32 - p.lag + 8 * np + 2 * t) & 31) * M_APITCH;
+                idoff[np][1] = ((base32 - p.lag + 8 * np + 2 * t + 1) & 31) * M_APITCH;
             }
 #pragma unroll
             for (int cw = 0; cw < CPW; ++cw) {
@@ -489,7 +490,7 @@ msca_sdm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
         // ================= write-out: O -> y, 32 bytes (16 channels) per pixel, both rows of a word =================
         {
             const int col = 4 * (warp / (NW / 8)) + (lane >> 3), rp = lane & 7, icol = w0c + col;
-            const int row_lo = 16 * s - M_P + 2 * rp;
+            const int row_lo = 16 * s - p.lag + 2 * rp;
             if (icol < W && row_lo + 1 >= 0 && row_lo < H) {
                 const uint32_t oa = sb + L::O_OFF + col * 32 + ((rp ^ (((col >> 2) & 1) * 4)) << 2);
                 uint32_t w[16];
@@ -543,7 +544,7 @@ msca_sdm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
 // Measured reason (ncu source view of the barrier-synchronised kernel above): with every warp in the same phase between two
 // __syncthreads the tensor / LSU / issue pipes take turns instead of overlapping (issue 28 %, HMMA 21 %), and the prefetched x
 // registers share scoreboards with the shared-memory loads of the MMA code, so LDSM consumers wait for global loads.
-constexpr int W_CT = 256, W_IO = 128, W_NT = W_CT + W_IO;
+constexpr int W_CT = 256;                       // compute threads; NIO = IO warps (4: 64 / 216 registers, 8: 48 / 208)
 
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {          // pinned where it is written (volatile): issue order = program order
     uint4 v;
@@ -551,13 +552,19 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {          // pinned w
     return v;
 }
 
-template <int K0, int K1, int K2, bool IDENT>
-__global__ void __launch_bounds__(W_NT, 1)
+template <int K0, int K1, int K2, bool IDENT, int NIO>
+__global__ void __launch_bounds__(W_CT + 32 * NIO, 1)
 msca_sdw_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, const float* __restrict__ w0, const float* __restrict__ b0,
                 const float* __restrict__ w1cat, const float* __restrict__ b1cat, const float* __restrict__ w2cat,
                 const float* __restrict__ b2cat, const float* __restrict__ res, const SdmParams p) {
     using L = Lay<K0, K1, K2>;
-    constexpr int NB = L::NB, CPW = 2;
+    constexpr int NB = L::NB, CPW = 2, W_IO = 32 * NIO, W_NT = W_CT + W_IO;
+    // setmaxnreg: an increase draws only from what this CTA released.  launch registers = 65536 / W_NT rounded down to 8:
+    //   NIO 4: 168 -> IO 64 (frees 128 x 104 = 13312), compute 216 (needs 256 x 48 = 12288)
+    //   NIO 8: 128 -> IO 48 (frees 256 x 80 = 20480),  compute 208 (needs 256 x 80 = 20480)
+    constexpr int REG_IO = NIO == 4 ? 64 : 48, REG_CT = NIO == 4 ? 216 : 208;
+    constexpr int XT = 40 / NIO;                                    // x staging tasks per IO warp (40 = 20 rows x 2 channel halves)
+    constexpr int XB = NIO == 4 ? 4 : 3;                            // rounds per batch (8 registers each)
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sb = ptx::smem_u32(smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
@@ -607,20 +614,19 @@ msca_sdw_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
     if (warp >= W_CT / 32) {
         // =========================================== IO warps ===========================================
         // Fragments are built by the compute warps from the O region: the first write-out happens long after (full_o of step 0).
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REG_IO));
         const int iw = warp - W_CT / 32, itid = tid - W_CT;
         const __nv_bfloat16* xb = x + (size_t)b * H * W * C;
         __nv_bfloat16* yb = y + (size_t)b * H * W * C;
         const int p2 = (res != nullptr && p.res_p > 0) ? min(H, p.res_p) : 0;
-        // x staging: warp task wt = iw + 4 r = (row, channel half hf), lane = column pair: pixels 2 lane, 2 lane + 1
+        // x staging: warp task wt = iw + NIO r = (row, channel half hf), lane = column pair: pixels 2 lane, 2 lane + 1
         const int xcol = w0c - 13 + 2 * lane;
         const bool xc0 = xcol >= 0 && xcol < W, xc1 = xcol + 1 >= 0 && xcol + 1 < W;
-        constexpr int XB = 4;                                           // rounds per batch (8 registers each)
         auto write_out = [&](int s) {
 #pragma unroll 1
-            for (int k = 0; k < 2; ++k) {
-                const int col = 4 * (iw + 4 * k) + (lane >> 3), rp = lane & 7, icol = w0c + col;
-                const int row_lo = 16 * s - M_P + 2 * rp;
+            for (int k = 0; k < 8 / NIO; ++k) {
+                const int col = 4 * (iw + NIO * k) + (lane >> 3), rp = lane & 7, icol = w0c + col;
+                const int row_lo = 16 * s - p.lag + 2 * rp;
                 if (icol < W && row_lo + 1 >= 0 && row_lo < H) {
                     const uint32_t oa = sb + L::O_OFF + col * 32 + ((rp ^ (((col >> 2) & 1) * 4)) << 2);
                     uint32_t w[16];
@@ -661,12 +667,12 @@ msca_sdw_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
         for (int s = 0; s < p.steps; ++s) {
             const int r0 = 16 * s - 2;
 #pragma unroll 1
-            for (int bt = 0; bt < 10; bt += XB) {
+            for (int bt = 0; bt < XT; bt += XB) {
                 uint4 xr[XB][2];
 #pragma unroll
                 for (int r = 0; r < XB; ++r) {
-                    const int wt = iw + 4 * (bt + r), row = r0 + (wt >> 1), hf = wt & 1;
-                    const bool rin = row >= 0 && row < H && bt + r < 10;
+                    const int wt = iw + NIO * (bt + r), row = r0 + (wt >> 1), hf = wt & 1;
+                    const bool rin = row >= 0 && row < H && bt + r < XT;
                     const __nv_bfloat16* src = xb + ((ptrdiff_t)row * W + xcol) * C + c0 + 8 * hf;
                     xr[r][0] = (rin && xc0) ? ldg_nc_v4(src) : make_uint4(0, 0, 0, 0);
                     xr[r][1] = (rin && xc1) ? ldg_nc_v4(src + C) : make_uint4(0, 0, 0, 0);
@@ -674,8 +680,8 @@ msca_sdw_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
                 if (bt == 0 && s > 0) ptx::mbar_wait(bar_ex, (s - 1) & 1);      // every compute warp has left conv0(s - 1)
 #pragma unroll
                 for (int r = 0; r < XB; ++r) {
-                    if (bt + r < 10) {
-                        const int wt = iw + 4 * (bt + r);
+                    if (bt + r < XT) {
+                        const int wt = iw + NIO * (bt + r);
                         const uint32_t a = sb + L::X_OFF + 8 * (wt & 1) * M_XPLANE + (wt >> 1) * M_XPITCH + lane * 4;
                         const uint32_t u0[4] = {xr[r][0].x, xr[r][0].y, xr[r][0].z, xr[r][0].w}, u1[4] = {xr[r][1].x, xr[r][1].y, xr[r][1].z, xr[r][1].w};
 #pragma unroll
@@ -696,8 +702,7 @@ msca_sdw_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
     }
 
     // =========================================== compute warps ===========================================
-    // the pool an increase draws from holds only what this CTA released: 128 x (168 - 64) = 13312 >= 256 x (216 - 168) = 12288
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REG_CT));
     unsigned long long bw0[CPW][5], bh[CPW][3][2], bv[CPW][3][2];
     float bias0[CPW], bias1[CPW][3], bias2[CPW][3];
 #pragma unroll
@@ -804,9 +809,9 @@ msca_sdw_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
 
         // per-step ring addresses (shared by the warp's channels)
         uint32_t st0[3] = {0, 0, 0}, st1[3] = {0, 0, 0}, va[3][3];
-        if constexpr (K0 > 0) sdm_ring_addrs<K0>(Br<K0>::RING == 32 ? base32 : base40, lane, g, t, st0[0], st1[0], va[0]);
-        if constexpr (K1 > 0) sdm_ring_addrs<K1>(Br<K1>::RING == 32 ? base32 : base40, lane, g, t, st0[1], st1[1], va[1]);
-        if constexpr (K2 > 0) sdm_ring_addrs<K2>(Br<K2>::RING == 32 ? base32 : base40, lane, g, t, st0[2], st1[2], va[2]);
+        if constexpr (K0 > 0) sdm_ring_addrs<K0>(Br<K0>::RING == 32 ? base32 : base40, p.lag, lane, g, t, st0[0], st1[0], va[0]);
+        if constexpr (K1 > 0) sdm_ring_addrs<K1>(Br<K1>::RING == 32 ? base32 : base40, p.lag, lane, g, t, st0[1], st1[1], va[1]);
+        if constexpr (K2 > 0) sdm_ring_addrs<K2>(Br<K2>::RING == 32 ? base32 : base40, p.lag, lane, g, t, st0[2], st1[2], va[2]);
         const bool rin0 = 16 * s + g < H, rin1 = 16 * s + g + 8 < H;
 
         // ================= hpass: a0 block -> T_k rows [16s, 16s+16) of every branch =================
@@ -831,8 +836,8 @@ msca_sdw_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
             uint32_t idoff[2][2];
 #pragma unroll
             for (int np = 0; np < 2; ++np) {
-                idoff[np][0] = ((base32 - M_P + 8 * np + 2 * t) & 31) * M_APITCH;
-                idoff[np][1] = ((base32 - M_P + 8 * np + 2 * t + 1) & 31) * M_APITCH;
+                idoff[np][0] = ((base32 - p.lag + 8 * np + 2 * t) & 31) * M_APITCH;
+                idoff[np][1] = ((base32 - p.lag + 8 * np + 2 * t + 1) & 31) * M_APITCH;
             }
 #pragma unroll
             for (int cw = 0; cw < CPW; ++cw) {
@@ -876,15 +881,15 @@ msca_sdw_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
     }
 }
 
-template <int K0, int K1, int K2, bool IDENT>
+template <int K0, int K1, int K2, bool IDENT, int NIO>
 int sdw_launch_k(const void* x, void* y, const float* w0, const float* b0, const float* w1cat, const float* b1cat, const float* w2cat,
                  const float* b2cat, const float* res, const SdmParams& p, cudaStream_t st) {
     using L = Lay<K0, K1, K2>;
     static std::atomic<unsigned long long> done{0};
-    CNA_CUDA(ensure_dyn_smem(msca_sdw_kernel<K0, K1, K2, IDENT>, L::TOTAL, done));
+    CNA_CUDA(ensure_dyn_smem(msca_sdw_kernel<K0, K1, K2, IDENT, NIO>, L::TOTAL, done));
     dim3 grid(p.strips * (p.C / 16), p.B);
-    msca_sdw_kernel<K0, K1, K2, IDENT><<<grid, W_NT, L::TOTAL, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, w0, b0, w1cat, b1cat, w2cat,
-                                                                    b2cat, res, p);
+    msca_sdw_kernel<K0, K1, K2, IDENT, NIO><<<grid, W_CT + 32 * NIO, L::TOTAL, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, w0, b0, w1cat,
+                                                                                    b1cat, w2cat, b2cat, res, p);
     CNA_LAUNCH_OK();
     return 0;
 }
@@ -907,14 +912,21 @@ int sdm_launch_t(const void* x, void* y, const float* w0, const float* b0, const
                  const float* b2cat, const float* res, const SdmParams& p, int max_smem, cudaStream_t st) {
     using L = Lay<K0, K1, K2>;
     if (L::TOTAL > max_smem) return -1;
-    // Measured on B200 (13 MSCAN-T blocks, batch 32): the warp-specialised kernel wins where the compute warps have work to hide the
-    // IO warps behind (three cascades: 1.03 vs 1.15 ms); a single cascade is bound by its four IO warps there (1.17 vs 1.07 ms).
-    // Diagnostic A/B switch: CNA_MSCA_WS=1 | 0 forces one of them.
+    // Measured on B200 (13 MSCAN-T blocks, batch 32): the warp-specialised kernel wins (three cascades: 0.98 vs 1.15 ms for the
+    // barrier-synchronised one; one cascade with 8 IO warps: 0.92 vs 1.02 ms).  Diagnostic A/B switch: CNA_MSCA_WS=0 runs the barrier kernel.
     static const int force = [] { const char* e = getenv("CNA_MSCA_WS"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
-    const bool ws = force >= 0 ? force == 1 : L::NB >= 2;
+    const bool ws = force >= 0 ? force == 1 : true;
+    // IO warps: a single cascade leaves the compute warps so little to do that four IO warps bind it (d1+fix, 13 blocks: 1.12 ms with 4,
+    // 0.92 ms with 8); three cascades are indifferent (0.98 / 0.99).  CNA_MSCA_NIO=4 | 8 forces one.
+    static const int nio_force = [] { const char* e = getenv("CNA_MSCA_NIO"); return e ? (e[0] == '8' ? 8 : 4) : 0; }();
+    const int nio = nio_force ? nio_force : (L::NB == 1 ? 8 : 4);
+    if (ws && nio == 8) {
+        return p.identity ? sdw_launch_k<K0, K1, K2, true, 8>(x, y, w0, b0, w1cat, b1cat, w2cat, b2cat, res, p, st)
+                          : sdw_launch_k<K0, K1, K2, false, 8>(x, y, w0, b0, w1cat, b1cat, w2cat, b2cat, res, p, st);
+    }
     if (ws) {
-        return p.identity ? sdw_launch_k<K0, K1, K2, true>(x, y, w0, b0, w1cat, b1cat, w2cat, b2cat, res, p, st)
-                          : sdw_launch_k<K0, K1, K2, false>(x, y, w0, b0, w1cat, b1cat, w2cat, b2cat, res, p, st);
+        return p.identity ? sdw_launch_k<K0, K1, K2, true, 4>(x, y, w0, b0, w1cat, b1cat, w2cat, b2cat, res, p, st)
+                          : sdw_launch_k<K0, K1, K2, false, 4>(x, y, w0, b0, w1cat, b1cat, w2cat, b2cat, res, p, st);
     }
     return p.identity ? sdm_launch_k<K0, K1, K2, 2, true>(x, y, w0, b0, w1cat, b1cat, w2cat, b2cat, res, p, st)
                       : sdm_launch_k<K0, K1, K2, 2, false>(x, y, w0, b0, w1cat, b1cat, w2cat, b2cat, res, p, st);
@@ -932,7 +944,8 @@ int msca_sdm_launch(const void* x, void* y, const float* w0, const float* b0, co
     SdmParams p{};
     p.B = B; p.H = H; p.W = W; p.C = C; p.identity = identity; p.res_p = res ? res_p : 0;
     p.strips = ceil_div(W, 32);
-    p.steps = ceil_div(H + M_P, 16);                                     // last step's output block [16s-10, 16s+6) covers row H-1
+    p.lag = H <= 16 ? 0 : M_P;                                           // a one-step image needs no lag: rows below it are the zeroed ring
+    p.steps = ceil_div(H + p.lag, 16);                                   // last step's output block [16s-lag, 16s-lag+16) covers row H-1
     DevInfo di;
     if (dev_info(&di)) return 1;
     const int k0 = ks_host[0], k1 = nb > 1 ? ks_host[1] : 0, k2 = nb > 2 ? ks_host[2] : 0;

@@ -71,6 +71,9 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--torch", action="store_true", help="also time stock torch/cuDNN on the GPU")
+    ap.add_argument("--block", action="store_true",
+                    help="also time the attention half of an MSCAN block (norm1 -> proj_1 -> GELU -> MSCA -> proj_2 -> + shortcut, "
+                         "layer scale, residual: models/mscan.py:72-80,108-109) fused into four kernels, and the same graph in torch/cuDNN")
     args = ap.parse_args()
     from approx import backend as B
     from approx.layers import MSCA
@@ -124,6 +127,48 @@ def main():
                    "min_traffic_GBps": 2 * elems * esz / ms / 1e6, "frac_hbm_min_traffic": 2 * elems * esz / ms / 1e6 / hbm}
             print(json.dumps(rec))
             total[name] = total.get(name, 0.0) + ms * nblk
+        if args.block and dt == torch.bfloat16:
+            from torch import nn
+            from approx.layers import MSCANAttention
+
+            class Attn(nn.Module):
+                def __init__(s_):
+                    super().__init__()
+                    s_.proj_1 = nn.Conv2d(C, C, 1)
+                    s_.spatial_gating_unit = MSCA(C, 5, (7, 11, 21))
+                    s_.proj_2 = nn.Conv2d(C, C, 1)
+
+            blk = MSCANAttention(nn.BatchNorm2d(C), Attn(), nn.Parameter(0.01 * torch.ones(C))).cuda().to(dt).eval()
+            with torch.no_grad():
+                blk.forward_nhwc(xs[0])
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    blk.forward_nhwc(xs[0])
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                with torch.cuda.graph(graph):
+                    keep = [blk.forward_nhwc(xi) for xi in xs]
+                ms = time_cuda(graph.replay, args.iters) / len(xs)
+                del keep, graph
+                # the same graph through stock torch modules (cuDNN / cuBLAS, channels_last bf16)
+                tm = torch_msca(C).cuda().to(dt).to(memory_format=torch.channels_last).eval()
+                bn = nn.BatchNorm2d(C).cuda().to(dt).eval()
+                p1, p2 = nn.Conv2d(C, C, 1).cuda().to(dt), nn.Conv2d(C, C, 1).cuda().to(dt)
+                ls = (0.01 * torch.ones(C, device="cuda", dtype=dt)).reshape(1, C, 1, 1)
+                xt = xs[0].permute(0, 3, 1, 2)
+
+                def torch_block():
+                    n = bn(xt)
+                    return xt + ls * (p2(tm(torch.nn.functional.gelu(p1(n)))) + n)
+                ms_t = time_cuda(torch_block, args.iters)
+            print(json.dumps({"bench": "mscan_attention_half", "dtype": args.dtype, "C": C, "H": H, "batch": args.batch, "ms": ms,
+                              "torch_cudnn_ms": ms_t, "speedup_over_torch": ms_t / ms, "kernels": 4,
+                              "min_traffic_GBps": 2 * elems * esz / ms / 1e6}))
+            total["attention_half_fused"] = total.get("attention_half_fused", 0.0) + ms * nblk
+            total["attention_half_torch_cudnn"] = total.get("attention_half_torch_cudnn", 0.0) + ms_t * nblk
         if args.torch:
             tm = torch_msca(C).cuda().to(dt).to(memory_format=torch.channels_last).eval()
             xt = x.permute(0, 3, 1, 2)

@@ -32,6 +32,7 @@ _SIGS = {
     "cna_conv1x1_tc_supported": "ii",
     "cna_conv1x1_pack": "ppiip",
     "cna_conv1x1_tc_forward": "pppppLiiip",
+    "cna_conv1x1_tc_forward_ex": "ppppppppLiiiip",
     "cna_lowrank1_fused_supported": "iiiiiiii",
     "cna_lowrank1_fused_forward": "pppppiiiiiiiip",
     "cna_fix_padding_bias": "ppiiiiiip",
@@ -278,6 +279,25 @@ def conv1x1_tc(x, w_nc, bias, relu=False, gate=None):
         assert gate.shape == y.shape and gate.dtype == x.dtype and gate.is_contiguous()
     with torch.cuda.device(x.device):
         _check(lib().cna_conv1x1_tc_forward(_p(x), _p(w_nc), _p(bias), _p(gate), _p(y), Bn * H * W, C, N, int(relu), _stream(x)))
+    return y
+
+
+def conv1x1_tc_ex(x, w_nc, bias, act="none", residual=None, alpha=None, beta=None, delta=None):
+    """1x1 conv on tcgen05 with the epilogues of an MSCAN attention block: y = act(x . w^T + bias), act in {none, relu, gelu}, and with
+    `residual` (same shape as y): y = alpha[n] * act(...) + beta[n] * residual + delta[n] (per-channel fp32 vectors or None)."""
+    _ready(x)
+    Bn, H, W, C = x.shape
+    N = w_nc.shape[0]
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and w_nc.shape == (N, C) and w_nc.dtype == torch.bfloat16
+    y = torch.empty((Bn, H, W, N), device=x.device, dtype=torch.bfloat16)
+    if residual is not None:
+        assert residual.shape == y.shape and residual.dtype == x.dtype and residual.is_contiguous()
+    for v in (alpha, beta, delta):
+        assert v is None or (v.dtype == torch.float32 and v.numel() == N and v.is_contiguous())
+    code = {"none": 0, "relu": 1, "gelu": 2}[act]
+    with torch.cuda.device(x.device):
+        _check(lib().cna_conv1x1_tc_forward_ex(_p(x), _p(w_nc), _p(bias), _p(residual), _p(alpha), _p(beta), _p(delta), _p(y),
+                                               Bn * H * W, C, N, code, 1 if residual is not None else 0, _stream(x)))
     return y
 
 

@@ -24,7 +24,9 @@ constexpr int kC1KC = 32;          // channels per K-chunk
 
 struct C1Params {
     long long P;       // pixels
-    int C, N, nkc, ntiles, stages, relu;
+    int C, N, nkc, ntiles, stages;
+    int act;           // 0 none, 1 ReLU, 2 GELU (erf form, nn.GELU default)
+    int aux_mode;      // what `gate` is: 0 multiplicative gate (y = bf16(v) * gate), 1 residual (y = alpha[n] v + beta[n] gate + delta[n])
     uint32_t off_a, a_stage, off_w, w_chunk, off_bias, off_bar;
 };
 
@@ -50,8 +52,8 @@ enum : int { C1_FULL = 0, C1_EMPTY = C1_FULL + kC1Stages, C1_WFULL = C1_EMPTY + 
 
 __global__ void __launch_bounds__(kC1Threads, 1)
 conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
-                  const float* __restrict__ bias, const __nv_bfloat16* __restrict__ gate, __nv_bfloat16* __restrict__ y,
-                  const C1Params p) {
+                  const float* __restrict__ bias, const __nv_bfloat16* __restrict__ gate, const float* __restrict__ alpha,
+                  const float* __restrict__ beta, const float* __restrict__ delta, __nv_bfloat16* __restrict__ y, const C1Params p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -69,7 +71,14 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc<512>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
-    for (int i = threadIdx.x; i < p.N; i += kC1Threads) sbias[i] = bias ? bias[i] : 0.f;
+    for (int i = threadIdx.x; i < p.N; i += kC1Threads) {
+        sbias[i] = bias ? bias[i] : 0.f;
+        if (p.aux_mode == 1) {          // per-channel affine of the residual epilogue: [alpha | beta | delta] after the bias
+            sbias[p.N + i] = alpha ? alpha[i] : 1.f;
+            sbias[2 * p.N + i] = beta ? beta[i] : 1.f;
+            sbias[3 * p.N + i] = delta ? delta[i] : 0.f;
+        }
+    }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -130,7 +139,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         const int lg = warp & 3;
         const uint32_t lane_addr = (uint32_t)(lg * 32) << 16;
         const int m = lg * 32 + lane;
-        const float lo = p.relu ? 0.f : -INFINITY;
+        const float lo = p.act == 1 ? 0.f : -INFINITY;
         // gate rows are fetched one 32-column chunk AHEAD (next chunk of this tile, or the first chunk of the warp's next tile):
         // with four epilogue warps per SM the global-load latency of a chunk would otherwise be exposed once per tile
         uint4 gq[4], gnext[4];
@@ -182,7 +191,21 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                     float f[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) f[i] = fmaxf(__uint_as_float(v[q * 8 + i]) + sbias[n0 + q * 8 + i], lo);
-                    if (grow) {
+                    if (p.act == 2) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) f[i] = 0.5f * f[i] * (1.f + erff(f[i] * 0.70710678118654752f));
+                    }
+                    if (grow && p.aux_mode == 1) {
+                        // residual epilogue: y = alpha[n] v + beta[n] res + delta[n] in fp32, one rounding
+                        const uint32_t g4[4] = {gq[q].x, gq[q].y, gq[q].z, gq[q].w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int n = n0 + q * 8 + 2 * i;
+                            const float r0 = __uint_as_float(g4[i] << 16), r1 = __uint_as_float(g4[i] & 0xffff0000u);
+                            f[2 * i] = sbias[p.N + n] * f[2 * i] + sbias[2 * p.N + n] * r0 + sbias[3 * p.N + n];
+                            f[2 * i + 1] = sbias[p.N + n + 1] * f[2 * i + 1] + sbias[2 * p.N + n + 1] * r1 + sbias[3 * p.N + n + 1];
+                        }
+                    } else if (grow) {
                         // the reference multiplies two materialised bf16 tensors: round the conv output first
                         const uint32_t g4[4] = {gq[q].x, gq[q].y, gq[q].z, gq[q].w};
 #pragma unroll
@@ -266,9 +289,22 @@ int cna_conv1x1_pack(const float* w_nc, void* packed, int N, int C, void* stream
     return 0;
 }
 
+int cna_conv1x1_tc_forward_ex(const void* a, const void* w_packed, const float* bias, const void* aux, const float* alpha,
+                              const float* beta, const float* delta, void* y, long long P, int C, int N, int act, int aux_mode,
+                              void* stream);
+
 int cna_conv1x1_tc_forward(const void* a, const void* w_packed, const float* bias, const void* gate, void* y, long long P, int C,
                            int N, int relu, void* stream) {
+    return cna_conv1x1_tc_forward_ex(a, w_packed, bias, gate, nullptr, nullptr, nullptr, y, P, C, N, relu ? 1 : 0, 0, stream);
+}
+
+int cna_conv1x1_tc_forward_ex(const void* a, const void* w_packed, const float* bias, const void* aux, const float* alpha,
+                              const float* beta, const float* delta, void* y, long long P, int C, int N, int act, int aux_mode,
+                              void* stream) {
+    const void* gate = aux;
     CNA_CHECK(a && w_packed && y && P > 0, "bad arguments");
+    CNA_CHECK(act >= 0 && act <= 2 && (aux_mode == 0 || aux_mode == 1), "bad epilogue selector");
+    CNA_CHECK(aux_mode == 0 || aux != nullptr, "residual epilogue without a residual tensor");
     CNA_CHECK(cna_conv1x1_tc_supported(C, N), "configuration not supported (needs C%32==0, N%16==0, N<=256, W resident in smem)");
     CNA_CHECK(P < (1LL << 31) * 128LL, "too many pixels");
     DevInfo di;
@@ -277,12 +313,12 @@ int cna_conv1x1_tc_forward(const void* a, const void* w_packed, const float* bia
     static std::atomic<unsigned long long> attr_done{0};
     CNA_CUDA(ensure_dyn_smem(conv1x1_tc_kernel, max_smem, attr_done));
     C1Params p{};
-    p.P = P; p.C = C; p.N = N; p.nkc = C / kC1KC; p.relu = relu;
+    p.P = P; p.C = C; p.N = N; p.nkc = C / kC1KC; p.act = act; p.aux_mode = aux_mode;
     p.ntiles = (int)((P + 127) / 128);
     p.a_stage = 128 * 64;
     p.w_chunk = ((uint32_t)N * 64 + 1023u) & ~1023u;
     const uint32_t wbytes = p.w_chunk * p.nkc;
-    const uint32_t bias_bytes = ((uint32_t)N * 4 + 1023u) & ~1023u;
+    const uint32_t bias_bytes = ((uint32_t)N * 16 + 1023u) & ~1023u;      // bias | alpha | beta | delta
     int stages = kC1Stages;
     while (stages > 2 && (size_t)wbytes + (size_t)stages * p.a_stage + bias_bytes + 2048 > (size_t)max_smem) --stages;
     CNA_CHECK((size_t)wbytes + (size_t)stages * p.a_stage + bias_bytes + 2048 <= (size_t)max_smem, "shared-memory plan does not fit");
@@ -293,7 +329,8 @@ int cna_conv1x1_tc_forward(const void* a, const void* w_packed, const float* bia
     if (c1_encode2d(&tm_a, a, (uint64_t)C, (uint64_t)P, kC1KC, 128)) return 1;
     if (c1_encode2d(&tm_w, w_packed, (uint64_t)C, (uint64_t)N, kC1KC, (uint32_t)N)) return 1;
     const int grid = std::min(p.ntiles, num_sms);
-    conv1x1_tc_kernel<<<grid, kC1Threads, smem, as_stream(stream)>>>(tm_a, tm_w, bias, (const __nv_bfloat16*)gate, (__nv_bfloat16*)y, p);
+    conv1x1_tc_kernel<<<grid, kC1Threads, smem, as_stream(stream)>>>(tm_a, tm_w, bias, (const __nv_bfloat16*)gate, alpha, beta, delta,
+                                                                     (__nv_bfloat16*)y, p);
     CNA_LAUNCH_OK();
     return 0;
 }

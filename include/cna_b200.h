@@ -79,6 +79,14 @@ int cna_conv1x1_tc_supported(int C, int N);
 int cna_conv1x1_pack(const float* w_nc, void* packed, int N, int C, void* stream);
 int cna_conv1x1_tc_forward(const void* a, const void* w_packed, const float* bias, const void* gate, void* y, long long P, int C,
                            int N, int relu, void* stream);
+/* The same kernel with the epilogues an MSCAN attention block needs around MSCA (src/approx/models/mscan.py:65-80, 108-110):
+ *   act: 0 none, 1 ReLU, 2 GELU (erf form, nn.GELU's default) on v = acc + bias[n];
+ *   aux_mode 0: aux = multiplicative gate (or NULL), y = bf16(v) * aux            — the call above;
+ *   aux_mode 1: aux = residual tensor, y = alpha[n] * v + beta[n] * aux + delta[n]  (fp32, one rounding; NULL arrays = 1, 1, 0):
+ *               proj_2 + shortcut + layer_scale_1 + the outer residual of MultiScaleConvAttnModule.forward in one epilogue. */
+int cna_conv1x1_tc_forward_ex(const void* a, const void* w_packed, const float* bias, const void* aux, const float* alpha,
+                              const float* beta, const float* delta, void* y, long long P, int C, int N, int act, int aux_mode,
+                              void* stream);
 
 /* ---- fused scheme-1 low-rank convolution (tcgen05) --------------------------------------------- */
 /* y = d_conv(s_conv(x)) in ONE kernel for bf16 NHWC tensors, stride 1, 'same' padding: the (B, C*M, H, W) intermediate of

@@ -420,3 +420,48 @@ def test_lowrank_exp_v1_app_alternating_and_init_methods():
     appr = LowRankExpV1(num_bases=(4,), max_iter=2, lmda_length=1, min_lmda=0.001, max_lmda=0.001, init_method='random')
     subr = appr.initialize(src); appr.optimize(subr)
     assert torch.isfinite(subr.new.d_conv.weight).all() and torch.isfinite(subr.new.s_conv.weight).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env", [{"CNA_MSCA_WS": "0"}, {"CNA_MSCA_NIO": "8"}, {"CNA_MSCA_NIO": "4"}, {"CNA_MSCA_SD": "f"}, {"CNA_MSCA_SD": "o"}])
+def test_msca_kernel_generations_agree_with_the_oracle(env):
+    """The kernel generations behind the diagnostic switches (barrier-synchronised mma.sync kernel, 4 / 8 IO warps, FFMA2 16-row
+    march, first-generation kernel) stay correct: each runs the original block and MscaRep d1+fix in its own process (the switches
+    are read once per process) against the bf16 oracle."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, io, contextlib, torch
+sys.path.insert(0, "convnet-approximater_b200"); sys.path.insert(0, ".")
+from oracle import approx_oracle as O
+from approx.layers import MSCA
+from approx.core import MscaRep
+torch.manual_seed(3)
+C, H, W = 32, 37, 45
+src = MSCA(C, 5, (7, 11, 21))
+x = torch.randn(2, C, H, W)
+dt = torch.bfloat16
+sd = {k: v.detach().to(dt) for k, v in src.state_dict().items()}
+br = [tuple(sd[f"sd_convs.branches.{i}.{n}"] for n in ("conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias")) for i in range(3)]
+ref = O.msca_forward(x.to(dt), sd["conv0.weight"], sd["conv0.bias"], lambda a: O.parallel_forward(a, br, True), sd["channel_mix.weight"], sd["channel_mix.bias"])
+import copy
+y = copy.deepcopy(src).cuda().to(dt).eval()(x.cuda().to(dt))
+e0 = O.compare4d(ref.float(), y.float().cpu())
+app = MscaRep(decomp=1, fix=True)
+sub = app.initialize(copy.deepcopy(src))
+with contextlib.redirect_stdout(io.StringIO()):
+    app.optimize(sub)
+tgt = app.postprocess(sub)
+# d1+fix: the bf16 kernel under test against this backend's fp32 kernels (a different code path, itself pinned by the golden tests)
+y1 = copy.deepcopy(tgt).cuda().to(dt).eval()(x.cuda().to(dt))
+y1f = copy.deepcopy(tgt).cuda().float().eval()(x.cuda())
+e1 = O.compare4d(y1f.float().cpu(), y1.float().cpu())
+print("ERR", e0, e1)
+assert e0 < 1e-3, e0
+assert e1 < 1e-2, e1
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env={**os.environ, **env},
+                       capture_output=True, text=True, timeout=200)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]

@@ -25,12 +25,12 @@
 // The NHWC <-> planar transposes are done in registers (PRMT): x rows of the NEXT step are fetched while the current one computes;
 // the output block is written out 32 bytes per pixel.
 //
-// Two kernels share the arithmetic (the host picks by measurement, sdm_launch_t):
-//   msca_sdw_kernel  warp-specialised: 8 compute warps (216 registers after setmaxnreg) + 4 IO warps (64) that do the transposes,
-//                    four mbarriers, no CTA-wide barrier in the loop.  Wins with three cascades.
-//   msca_sdm_kernel  8 warps that all do everything, two __syncthreads per step.  Wins with one cascade (MscaRep rank 1).
+// Two kernels share the arithmetic (sdm_launch_t):
+//   msca_sdw_kernel  warp-specialised (shipped): 8 compute warps (216 | 208 registers after setmaxnreg) + 4 | 8 IO warps (64 | 48)
+//                    that do the transposes, four mbarriers, no CTA-wide barrier in the loop.  8 IO warps for a single cascade.
+//   msca_sdm_kernel  8 warps that all do everything, two __syncthreads per step (kept behind CNA_MSCA_WS=0 as the A/B reference).
 // Measured on B200 (13 MSCAN-T blocks at 512 x 512, batch 32, bf16, one CUDA graph; profiles/r02_msca_mma.txt): original block
-// 1.75 ms (FFMA2 kernel, msca16.cu) -> 0.98 ms, MscaRep d1+fix 1.34 -> 1.02 ms.  ncu of the (32 ch, 128 x 128) launch: 96 us against 197;
+// 1.75 ms (FFMA2 kernel, msca16.cu) -> 0.97 ms, MscaRep d1+fix 1.34 -> 0.90 ms.  ncu of the (32 ch, 128 x 128) launch: 96 us against 197;
 // HMMA pipe 25 % active, issue 34 %: the kernel is bound by per-warp dependent latency (ldmatrix -> HMMA -> cvt -> st.shared chains,
 // 7.8 cycles per instruction and warp with 2 compute warps per scheduler) and by the 255-register ceiling that keeps it at 8 compute
 // warps, not by a pipe.  Rejected by measurement: 16 warps x 1 channel at 128 registers (spills; 1.28 ms), own ldmatrix loads for the

@@ -18,7 +18,7 @@
 namespace cna {
 using namespace ptx;
 
-constexpr int kC1Threads = 192;
+constexpr int kC1Threads = 320;     // warp 0 TMA, warp 1 MMA, warps 2-5 / 6-9: two epilogue groups, each on its half of the N columns
 constexpr int kC1Stages = 8;
 constexpr int kC1KC = 32;          // channels per K-chunk
 
@@ -67,7 +67,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         prefetch_tmap(&tm_a); prefetch_tmap(&tm_w);
         for (int i = 0; i < kC1Stages; ++i) { mbar_init(bar(C1_FULL + i), 1); mbar_init(bar(C1_EMPTY + i), 1); }
         mbar_init(bar(C1_WFULL), 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(bar(C1_ACC_FULL + i), 1); mbar_init(bar(C1_ACC_EMPTY + i), 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar(C1_ACC_FULL + i), 1); mbar_init(bar(C1_ACC_EMPTY + i), 256); }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc<512>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
@@ -140,22 +140,27 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         const uint32_t lane_addr = (uint32_t)(lg * 32) << 16;
         const int m = lg * 32 + lane;
         const float lo = p.act == 1 ? 0.f : -INFINITY;
+        // Two epilogue groups (warps 2-5, 6-9) split the N columns of every tile: with K = C <= 256 the GEMM is a few hundred cycles
+        // and ONE group's ld -> math -> 32-byte stores chain per 32 columns bounded the kernel (40 us for 100 MB at C = 32).
+        const int eg = warp >= 6 ? 1 : 0;
+        const int half = ((p.N / 2 + 15) / 16) * 16;                  // columns of group 0, a multiple of 16
+        const int c_lo = eg ? half : 0, c_hi = eg ? p.N : half;
         // gate rows are fetched one 32-column chunk AHEAD (next chunk of this tile, or the first chunk of the warp's next tile):
-        // with four epilogue warps per SM the global-load latency of a chunk would otherwise be exposed once per tile
+        // the global-load latency of a chunk would otherwise be exposed once per tile
         uint4 gq[4], gnext[4];
         auto gate_fetch = [&](int it, int n0, uint4 (&dst)[4]) {
             const long long r = (long long)(first + it * step) * 128 + m;
             if (gate && it < my_tiles && r < p.P) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
-                    if (n0 + q * 8 < p.N) {      // volatile: the load is issued HERE, not sunk down to its first use
+                    if (n0 + q * 8 < c_hi) {      // volatile: the load is issued HERE, not sunk down to its first use
                         asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
                                      : "=r"(dst[q].x), "=r"(dst[q].y), "=r"(dst[q].z), "=r"(dst[q].w)
                                      : "l"(reinterpret_cast<const uint4*>(gate + r * p.N + n0) + q));
                     }
             }
         };
-        gate_fetch(0, 0, gnext);
+        gate_fetch(0, c_lo, gnext);
         for (int it = 0; it < my_tiles; ++it) {
             const int buf = it & 1;
             const long long row = (long long)(first + it * step) * 128 + m;
@@ -164,26 +169,30 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             const bool ok = row < p.P;
             const __nv_bfloat16* grow = gate ? gate + row * p.N : nullptr;
             __nv_bfloat16* yrow = y + row * p.N;
-            for (int n0 = 0; n0 < p.N; n0 += 32) {
+            if (c_lo >= c_hi) {          // N = 16: group 1 owns no columns, but the accumulator barrier counts its threads
+                tc_fence_before_sync();
+                mbar_arrive(bar(C1_ACC_EMPTY + buf));
+            }
+            for (int n0 = c_lo; n0 < c_hi; n0 += 32) {
                 uint32_t v[32];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) gq[q] = gnext[q];
-                if (n0 + 32 < p.N) gate_fetch(it, n0 + 32, gnext);
-                else gate_fetch(it + 1, 0, gnext);
-                if (n0 + 32 <= p.N) {
+                if (n0 + 32 < c_hi) gate_fetch(it, n0 + 32, gnext);
+                else gate_fetch(it + 1, c_lo, gnext);
+                if (n0 + 32 <= c_hi) {
                     tmem_ld32(tmem + buf * 256 + lane_addr + n0, v);
-                } else {   // N % 32 == 16
+                } else {   // a 16-column tail
                     tmem_ld16(tmem + buf * 256 + lane_addr + n0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
 #pragma unroll
                     for (int i = 16; i < 32; ++i) v[i] = 0;
                 }
                 tmem_ld_wait();
-                if (n0 + 32 >= p.N) {
+                if (n0 + 32 >= c_hi) {
                     tc_fence_before_sync();
                     mbar_arrive(bar(C1_ACC_EMPTY + buf));      // accumulator drained
                 }
                 if (!ok) continue;
-                const int nvalid = min(32, p.N - n0);
+                const int nvalid = min(32, c_hi - n0);
                 uint4 pend = make_uint4(0, 0, 0, 0);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {

@@ -45,6 +45,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 #include <mutex>
+#include <algorithm>
 
 namespace cna {
 using namespace ptx;
@@ -77,8 +78,9 @@ struct LR2Params {
     uint32_t off_x, x_stage;      // x ring
     uint32_t off_v, v_chunk;      // Wv chunks (resident: nch of them; streamed: one per x stage)
     uint32_t off_h, h_slot;       // Wh tap slots (resident: nn2*3; streamed: hslots)
-    uint32_t off_y;               // y staging (2 x kYBuf, one per epilogue group)
-    uint32_t off_p;               // pooled staging (2 x 4 KB), only when pool
+    uint32_t off_y;               // y staging: kYBuf x (pool ? 1 : nystg) per epilogue group
+    uint32_t off_p;               // pooled staging: 4 KB x nystg per epilogue group, only when pool
+    int nystg;                    // TMA-store source buffers per epilogue group = stores a group keeps in flight (1..4)
     uint32_t off_bias, off_bar;
     // optional: the T-epilogue also writes bf16 T = v_conv(x) to global memory (element strides: image, tile-row axis, tile-col
     // axis); t_only = 1 skips GEMM2 and the y path altogether (a plain 3-tap C -> KP convolution along the tile-row axis)
@@ -103,6 +105,23 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 // loads of the following chunks above the store instead of serialising load -> math -> store eight times.
 __device__ __forceinline__ void st_shared_v4_relaxed(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
+}
+// (a + b) on two fp32 lanes at once (SASS FADD2), then one rounding to a bf16 pair — same arithmetic as two scalar adds
+__device__ __forceinline__ uint32_t add2_pack_bf16(uint32_t a0, uint32_t a1, float b0, float b1) {
+#ifdef CNA_LR2_FADD2
+    unsigned long long ra = (unsigned long long)a0 | ((unsigned long long)a1 << 32), rd;
+    unsigned long long rb = (unsigned long long)__float_as_uint(b0) | ((unsigned long long)__float_as_uint(b1) << 32);
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return pack_bf16(__uint_as_float((uint32_t)rd), __uint_as_float((uint32_t)(rd >> 32)));
+#else
+    return pack_bf16(__uint_as_float(a0) + b0, __uint_as_float(a1) + b1);
+#endif
+}
+// ReLU on a packed bf16 pair: rounding is monotone, so max(round(v), 0) == round(max(v, 0))
+__device__ __forceinline__ uint32_t relu_bf16x2(uint32_t v) {
+    uint32_t d;
+    asm("max.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(v), "r"(0u));
+    return d;
 }
 __device__ __forceinline__ float4 ld_shared_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 // volatile (keeps its place among the other volatile asm statements, i.e. stays where the software pipeline put it), no memory clobber
@@ -142,7 +161,10 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, const LR2Params& p) {
     return {b, th * kTileRows, tw * kValidCols};
 }
 
-template <int CK, int KP, int NT2>
+// TRACE = true compiles the per-tile clock stamps in (benchmarks/trace_lowrank2.py); the production instances carry none: the
+// predicated-off stamp code was ~10 % of the instructions the epilogue warps issue per tile, and layer 1 / the K <= 32 forms are
+// bound by exactly that issue rate (profiles/r02_fused_conv_l1_ncu.txt).
+template <int CK, int KP, int NT2, bool TRACE = false>
 __global__ void __launch_bounds__(kThreads, 1)
 lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_wv,
                       const __grid_constant__ CUtensorMap tm_wh, const __grid_constant__ CUtensorMap tm_y,
@@ -188,6 +210,7 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
 
     // diagnostic: row `trace_tiles` of the trace holds {clock64, globaltimer} at CTA 0's start and end (effective SM clock)
     auto stamp_wall = [&](int slot) {
+        if constexpr (!TRACE) return;
         if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
             unsigned long long gt;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -199,6 +222,7 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     const int first = blockIdx.x, step = gridDim.x;
     const int my_tiles = first < p.ntiles ? (p.ntiles - first + step - 1) / step : 0;
     auto stamp = [&](int it, int ev) {
+        if constexpr (!TRACE) return;
         if (p.trace != nullptr && blockIdx.x == 0 && it >= p.trace_skip && it < p.trace_skip + p.trace_tiles)
             p.trace[(it - p.trace_skip) * kTraceEv + ev] = clock64();
     };
@@ -448,9 +472,12 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         const bool valid = xc >= 1 && xc <= kValidCols;
         const uint32_t srow = (uint32_t)(r * kValidCols + (xc - 1));      // staging row (TMA box order: row, col)
         const uint32_t row_off = srow * 128u, sw = srow & 7u;             // 128B-swizzle: chunk ^= row & 7
-        const float lo = p.relu ? 0.f : -INFINITY;
-        const uint32_t sb = base + p.off_y + g * kYBuf;
-        const uint32_t pb = base + p.off_p + g * 4096;
+        // The store of an item drains for ~1500-2100 cycles once every SM is writing (profiles/r02_fused_conv_trace.txt), so a group
+        // cycles through p.nystg source buffers and only waits for the store issued nystg items ago.
+        const int nys = p.nystg;
+        const uint32_t sb0 = base + p.off_y + g * (p.pool ? 1 : nys) * kYBuf;
+        const uint32_t pb0 = base + p.off_p + g * nys * 4096;
+        int bi = 0;
         const int nq = p.t_only ? 0 : my_tiles * p.nn2;
         const int q0 = NT2 == 64 ? g : 0, qstep = NT2 == 64 ? 2 : 1;
         int j = 0, n2 = q0;                      // q = j * nn2 + n2
@@ -477,7 +504,14 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             mbar_arrive(bar(BAR_YACC_EMPTY + yb));       // accumulator drained: GEMM2 of N-tile q+2 may start
             // this group's staging buffer was handed to a TMA store one item ago: make sure it has been read
             // (waited for here, after the TMEM load, so that the store's smem read overlaps the load)
-            if (et == 0) tma_store_wait_read<0>();
+            if (et == 0) {
+                if (nys == 1) tma_store_wait_read<0>();
+                else if (nys == 2) tma_store_wait_read<1>();
+                else if (nys == 3) tma_store_wait_read<2>();
+                else tma_store_wait_read<3>();
+            }
+            const uint32_t sb = sb0 + (p.pool ? 0 : bi) * kYBuf, pb = pb0 + bi * 4096;
+            if (++bi == nys) bi = 0;
             named_bar_sync(bar_a, 128);
             if (et == 0 && n2 == 0) stamp(j, 14);
             if (valid && !(p.debug & 2)) {
@@ -494,11 +528,10 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                         bq[(2 * ch) & 3] = ld_shared_f4_relaxed(bz + (ch + 2) * 32);
                         bq[(2 * ch + 1) & 3] = ld_shared_f4_relaxed(bz + (ch + 2) * 32 + 16);
                     }
-                    st_shared_v4_relaxed(sb + row_off + (((uint32_t)ch ^ sw) << 4),
-                                         pack_bf16(fmaxf(__uint_as_float(v[ch * 8 + 0]) + b0.x, lo), fmaxf(__uint_as_float(v[ch * 8 + 1]) + b0.y, lo)),
-                                         pack_bf16(fmaxf(__uint_as_float(v[ch * 8 + 2]) + b0.z, lo), fmaxf(__uint_as_float(v[ch * 8 + 3]) + b0.w, lo)),
-                                         pack_bf16(fmaxf(__uint_as_float(v[ch * 8 + 4]) + b1.x, lo), fmaxf(__uint_as_float(v[ch * 8 + 5]) + b1.y, lo)),
-                                         pack_bf16(fmaxf(__uint_as_float(v[ch * 8 + 6]) + b1.z, lo), fmaxf(__uint_as_float(v[ch * 8 + 7]) + b1.w, lo)));
+                    uint32_t o0 = add2_pack_bf16(v[ch * 8 + 0], v[ch * 8 + 1], b0.x, b0.y), o1 = add2_pack_bf16(v[ch * 8 + 2], v[ch * 8 + 3], b0.z, b0.w);
+                    uint32_t o2 = add2_pack_bf16(v[ch * 8 + 4], v[ch * 8 + 5], b1.x, b1.y), o3 = add2_pack_bf16(v[ch * 8 + 6], v[ch * 8 + 7], b1.z, b1.w);
+                    if (p.relu) { o0 = relu_bf16x2(o0); o1 = relu_bf16x2(o1); o2 = relu_bf16x2(o2); o3 = relu_bf16x2(o3); }
+                    st_shared_v4_relaxed(sb + row_off + (((uint32_t)ch ^ sw) << 4), o0, o1, o2, o3);
                 }
             }
             if (!p.pool) {
@@ -624,21 +657,24 @@ static int pick_ck(int c_pad) { return c_pad % 64 == 0 ? 64 : (c_pad % 32 == 0 ?
 static int pick_nt2(int N) { return N % 128 == 0 ? 128 : 64; }
 static uint32_t up1k(uint32_t v) { return (v + 1023u) & ~1023u; }
 
-// Fills the smem plan; returns total dynamic smem bytes (incl. 1 KB alignment slack) or 0 if it cannot fit.
-static size_t plan_smem(LR2Params& p, int CK, int KP, int NT2, size_t limit) {
-    const uint32_t pool_bytes = p.pool ? 2 * 4096 : 0;
+// Fills the smem plan for `ystg` store buffers per epilogue group; returns total dynamic smem bytes (incl. 1 KB alignment slack)
+// or 0 if it cannot fit.
+static size_t plan_smem_ystg(LR2Params& p, int CK, int KP, int NT2, size_t limit, int ystg) {
+    const uint32_t pool_bytes = p.pool ? 2 * ystg * 4096 : 0;
+    const uint32_t ybytes = up1k((p.pool ? 2 : 2 * ystg) * kYBuf);
     const uint32_t xrow = CK * 2, hrow = KP * 2;
+    p.nystg = ystg;
     p.x_stage = up1k(kXRows * kTileCols * xrow);
     p.v_chunk = up1k(3 * KP * xrow);
     p.h_slot = up1k(NT2 * hrow);
-    const uint32_t fixed = up1k(2 * kYBuf) + pool_bytes + up1k(p.N * 4) + 1024 /*barriers*/ + 1024 /*align slack*/;
+    const uint32_t fixed = ybytes + pool_bytes + up1k(p.N * 4) + 1024 /*barriers*/ + 1024 /*align slack*/;
     auto layout = [&](int resident, int stages, int hslots) {
         p.resident = resident; p.stages = stages; p.hslots = hslots;
         uint32_t o = 0;
         p.off_x = o; o += stages * p.x_stage;
         p.off_v = o; o += (resident ? p.nch : stages) * p.v_chunk;
         p.off_h = o; o += (resident ? 3 * p.nn2 : hslots) * p.h_slot;
-        p.off_y = o; o += up1k(2 * kYBuf);
+        p.off_y = o; o += ybytes;
         p.off_p = o; o += pool_bytes;
         p.off_bias = o; o += up1k(p.N * 4);
         p.off_bar = o;
@@ -659,6 +695,27 @@ static size_t plan_smem(LR2Params& p, int CK, int KP, int NT2, size_t limit) {
     return 0;
 }
 
+// Store-buffer depth: the deepest (<= kAutoYStg) that costs the plan neither its resident weights nor an x stage nor Wh slots below
+// a tile's worth; CNA_LR2_YSTG forces a depth (diagnostic sweeps), falling back towards 1 if it does not fit at all.
+constexpr int kAutoYStg = 3;
+static size_t plan_smem(LR2Params& p, int CK, int KP, int NT2, size_t limit) {
+    static const int forced = [] { const char* e = getenv("CNA_LR2_YSTG"); return e ? std::max(1, std::min(4, atoi(e))) : 0; }();
+    if (forced) {
+        for (int y = forced; y >= 1; --y) { size_t s = plan_smem_ystg(p, CK, KP, NT2, limit, y); if (s) return s; }
+        return 0;
+    }
+    LR2Params base = p;
+    size_t s1 = plan_smem_ystg(base, CK, KP, NT2, limit, 1);
+    if (!s1) return 0;
+    for (int y = kAutoYStg; y >= 2; --y) {
+        LR2Params q = p;
+        size_t s = plan_smem_ystg(q, CK, KP, NT2, limit, y);
+        if (s && q.resident == base.resident && q.stages >= base.stages && (q.resident || q.hslots >= std::min(base.hslots, 3 * p.nn2))) { p = q; return s; }
+    }
+    p = base;
+    return s1;
+}
+
 static bool shape_ok(int H, int W, int c_pad, int k_pad, int N, int d) {
     return d == 3 && H >= 1 && W >= 1 && c_pad >= 16 && c_pad % 16 == 0 && (k_pad == 16 || k_pad == 32 || k_pad == 64) &&
            N >= 64 && N % 64 == 0 && N / 64 <= kMaxNTiles;
@@ -671,6 +728,18 @@ using namespace cna;
 template <int CKV, int KPV, int NT2V>
 static int lr2_launch_one(int grid, size_t smem, int max_smem, cudaStream_t st, const CUtensorMap& tm_x, const CUtensorMap& tm_wv,
                           const CUtensorMap& tm_wh, const CUtensorMap& tm_y, const float* bias, const LR2Params& p) {
+    if (p.trace != nullptr) {
+        // traced instances exist for the configurations the trace tool is used on (each one is a full extra compile)
+        constexpr bool kTraced = (KPV == 64 && (CKV == 16 || CKV == 64)) || (KPV == 16 && CKV == 64 && NT2V == 64);
+        if constexpr (kTraced) {
+            static std::atomic<unsigned long long> attr_done_t{0};
+            CNA_CUDA(ensure_dyn_smem(lowrank2_fused_kernel<CKV, KPV, NT2V, true>, max_smem, attr_done_t));
+            lowrank2_fused_kernel<CKV, KPV, NT2V, true><<<grid, kThreads, smem, st>>>(tm_x, tm_wv, tm_wh, tm_y, bias, p);
+            return 0;
+        } else {
+            CNA_CHECK(false, "no traced instance of the fused kernel for this (channel chunk, rank, N-tile) combination");
+        }
+    }
     static std::atomic<unsigned long long> attr_done{0};
     CNA_CUDA(ensure_dyn_smem(lowrank2_fused_kernel<CKV, KPV, NT2V>, max_smem, attr_done));
     lowrank2_fused_kernel<CKV, KPV, NT2V><<<grid, kThreads, smem, st>>>(tm_x, tm_wv, tm_wh, tm_y, bias, p);

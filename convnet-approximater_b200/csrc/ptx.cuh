@@ -54,10 +54,29 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
         : "memory");
     return ok;
 }
-// Blocks until the phase with the given parity has completed (try_wait suspends in hardware between polls).
+// Blocks until the phase with the given parity has completed.  The suspend-time hint lets the hardware park the warp until the
+// phase flips (or ~10 ms pass) instead of returning after ~20 cycles: without it every waiting warp of a warp-specialised kernel
+// re-issued a 5-instruction poll loop at ~0.2 IPC and took issue slots from the epilogue warps of its sub-partition (ncu source view
+// of the fused conv, profiles/r02_fused_conv_l1_ncu.txt: 1300 of 4470 warp instructions per tile were poll loops).
+#ifndef CNA_MBAR_HINT_NS
+#define CNA_MBAR_HINT_NS 0x989680
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#ifdef CNA_MBAR_NO_HINT
     while (!mbar_try_wait(bar, parity)) {
     }
+    return;
+#endif
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity), "r"((uint32_t)CNA_MBAR_HINT_NS)
+        : "memory");
 }
 
 // 32-byte global store (STG.E.256 on sm_100a): one write transaction per full sector where a thread owns 32 contiguous bytes

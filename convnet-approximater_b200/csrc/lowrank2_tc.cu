@@ -161,6 +161,23 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, const LR2Params& p) {
     return {b, th * kTileRows, tw * kValidCols};
 }
 
+// (image, tile row, tile column) of a CTA's current tile plus the decomposition of the grid stride: advancing costs a few additions
+struct TileStep { int b, th, tw, db, dth, dtw; };
+__device__ __forceinline__ TileStep tile_step_init(int first, int step, const LR2Params& p) {
+    const int per_img = p.tiles_w * p.tiles_h;
+    TileStep t;
+    t.b = first / per_img; int rem = first - t.b * per_img;
+    t.th = rem / p.tiles_w; t.tw = rem - t.th * p.tiles_w;
+    t.db = step / per_img; rem = step - t.db * per_img;
+    t.dth = rem / p.tiles_w; t.dtw = rem - t.dth * p.tiles_w;
+    return t;
+}
+__device__ __forceinline__ void tile_step_advance(TileStep& t, const LR2Params& p) {
+    t.tw += t.dtw; t.th += t.dth; t.b += t.db;
+    if (t.tw >= p.tiles_w) { t.tw -= p.tiles_w; ++t.th; }
+    if (t.th >= p.tiles_h) { t.th -= p.tiles_h; ++t.b; }
+}
+
 // TRACE = true compiles the per-tile clock stamps in (benchmarks/trace_lowrank2.py); the production instances carry none: the
 // predicated-off stamp code was ~10 % of the instructions the epilogue warps issue per tile, and layer 1 / the K <= 32 forms are
 // bound by exactly that issue rate (profiles/r02_fused_conv_l1_ncu.txt).
@@ -481,9 +498,11 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         const int nq = p.t_only ? 0 : my_tiles * p.nn2;
         const int q0 = NT2 == 64 ? g : 0, qstep = NT2 == 64 ? 2 : 1;
         int j = 0, n2 = q0;                      // q = j * nn2 + n2
-        while (n2 >= p.nn2 && j < my_tiles) { n2 -= p.nn2; ++j; }
+        // tile coordinates of tile j, advanced by additions (a decode per item is two integer divisions = ~170 instructions in
+        // every epilogue warp, and only the storing thread needs the result)
+        TileStep tc = tile_step_init(first, step, p);
+        while (n2 >= p.nn2 && j < my_tiles) { n2 -= p.nn2; ++j; tile_step_advance(tc, p); }
         for (int q = q0; q < nq; q += qstep) {
-            TileCoord t = decode_tile(first + j * step, p);
             const int yb = q & 1;
             const int chan0 = NT2 == 64 ? n2 * 64 : n2 * 128 + g * 64;
             mbar_wait(bar(BAR_YACC_FULL + yb), (uint32_t)((q >> 1) & 1));
@@ -541,7 +560,7 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 named_bar_sync(bar_b, 128);
                 if (et == 0 && n2 == 0) stamp(j, 15);
                 if (et == 0 && !(p.debug & 1)) {
-                    tma_store_4d(&tm_y, sb, chan0, t.w0, t.h0, t.b);
+                    tma_store_4d(&tm_y, sb, chan0, tc.tw * kValidCols, tc.th * kTileRows, tc.b);
                     tma_store_commit();
                     if (n2 == p.nn2 - 1) stamp(j, 9);
                 }
@@ -577,13 +596,13 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 fence_proxy_async_smem();
                 named_bar_sync(bar_c, 128);
                 if (et == 0 && !(p.debug & 1)) {
-                    tma_store_4d(&tm_y, pb, chan0, t.w0 >> 1, t.h0 >> 1, t.b);
+                    tma_store_4d(&tm_y, pb, chan0, (tc.tw * kValidCols) >> 1, (tc.th * kTileRows) >> 1, tc.b);
                     tma_store_commit();
                     if (n2 == p.nn2 - 1) stamp(j, 9);
                 }
             }
             n2 += qstep;
-            while (n2 >= p.nn2) { n2 -= p.nn2; ++j; }
+            while (n2 >= p.nn2) { n2 -= p.nn2; ++j; tile_step_advance(tc, p); }
         }
         if (et == 0) tma_store_wait_all<0>();
     }

@@ -43,6 +43,22 @@ def layer_bytes(i, K):
     return 2 * H * H * C + 2 * out_px * N + 2 * 3 * K * (C + N) + 2 * N
 
 
+def layer_write_bytes(i):
+    """Output bytes of layer i per image (the part of layer_bytes that is written)."""
+    C, N, H = VGG[i]
+    return 2 * (H * H // 4 if i in POOLED else H * H) * N
+
+
+def measure_write_peak(dev, nbytes=1644167168, iters=10):
+    """Write-only HBM bandwidth of this GPU in GB/s: a device memset of a buffer the size of layer 1's output (1.64 GB, 13x the
+    L2), timed with CUDA events.  MEASURED_PEAKS.json's figure is a COPY (half reads, half writes); the write direction alone
+    stops at ~60 % of it (profiles/r02_hbm_write_peak.txt), which is what bounds a layer that writes 4x what it reads."""
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    ms = _time_cuda(lambda: buf.zero_(), iters, warmup=3)
+    del buf
+    return nbytes / ms / 1e6
+
+
 def algorithmic_bytes_per_image(K):
     return sum(layer_bytes(i, K) for i in range(len(VGG)))
 
@@ -493,6 +509,7 @@ def run_ours(args):
         pass
     del trunk, x_dev, pipe
     torch.cuda.empty_cache()
+    write_peak = measure_write_peak(dev) if rank == 0 else None
     msca_rec = recon_rec = None
     if not args.no_msca:
         msca_rec = bench_msca(dev, peaks_all, batch=32, iters=10)
@@ -533,11 +550,12 @@ def run_ours(args):
         tflops = alg_flops * args.steps / (conv_ms * 1e-3) / 1e12
         # which roof binds: per layer the larger of (bytes / HBM peak) and (flops / sustained tensor peak); the step's bound is
         # the sum of those floors, and the step is labelled by the term that contributes more of it
-        t_hbm = t_tc = floor_s = 0.0
+        t_hbm = t_tc = floor_s = floor_w_s = 0.0
         for i, (C, N, H) in enumerate(VGG):
             fb = layer_bytes(i, K) * Bsz / (hbm_peak * 1e9)
             ft = 6 * H * H * K * (C + N) * Bsz / (tc_peak * 1e12)
             floor_s += max(fb, ft)
+            floor_w_s += max(fb, ft, layer_write_bytes(i) * Bsz / (write_peak * 1e9))
             if fb >= ft:
                 t_hbm += fb
             else:
@@ -571,6 +589,9 @@ def run_ours(args):
             "tensor_frac_of_sustained_peak": tflops / tc_peak,
             "per_layer_floor_ms": floor_s * 1e3, "frac_of_per_layer_floor": floor_s / conv_s_per_step,
             "floor_share": {"hbm_bound_layers_ms": t_hbm * 1e3, "tensor_bound_layers_ms": t_tc * 1e3},
+            "write_only_peak_GBps": write_peak,
+            "write_only_peak_source": "device memset of 1.64 GB timed in this run (the copy peak is half reads, half writes)",
+            "per_layer_floor_write_aware_ms": floor_w_s * 1e3, "frac_of_write_aware_floor": floor_w_s / conv_s_per_step,
             "fused_conv_share_of_step": conv_ms / ms,
             "value_note": "`value` times forward_nhwc on a device-resident NHWC input already padded to 16 channels; the NCHW->NHWC "
                           "layout kernel of the module path is inside `e2e`, not inside `value`"})

@@ -14,6 +14,7 @@
 #include "common.cuh"
 
 #include <stdlib.h>
+#include <type_traits>
 
 namespace cna {
 
@@ -329,6 +330,10 @@ template <typename T>
 static int dw_tile_dispatch(int kh, int kw, const void* x, const void* w, const float* bias, const float* res, int res_p, const void* add,
                             void* y, int B, int H, int W, int C, cudaStream_t st, bool* handled) {
     *handled = true;
+    if (std::is_same<T, __nv_bfloat16>::value && res == nullptr && add == nullptr && (kh == 1 || kw == 1)) {
+        const int rc = dw_strip_tma_try(x, w, bias, y, B, H, W, C, kh, kw, st);      // TMA-fed shared-memory pipeline (dwstrip_tma.cu)
+        if (rc >= 0) return rc;
+    }
     if (getenv("CNA_DW_NO_STRIP") == nullptr) {      // (diagnostic switch: use the smem-tiled kernel for strips too)
 #define CNA_STRIP_CASE(KV) \
         if (kh == 1 && kw == KV) { const int rc = dw_strip_launch_t<T, KV, true>(x, w, bias, res, res_p, add, y, B, H, W, C, st); if (rc >= 0) return rc; } \

@@ -110,6 +110,15 @@ DW_CASES = [
     (2, 32, 17, 50, 1, 1, 21, 1, 1, 0, 10),
     (2, 160, 32, 32, 1, 21, 1, 1, 1, 10, 0),
     (2, 32, 18, 18, 1, 3, 3, 1, 1, 1, 1),
+    # TMA-pipelined strips (dwstrip_tma.cu, bf16): several tiles per axis, ragged edges, every strip length it is built for
+    (3, 64, 70, 75, 1, 1, 7, 1, 1, 0, 3),
+    (3, 64, 70, 75, 1, 21, 1, 1, 1, 10, 0),
+    (2, 32, 33, 65, 1, 1, 3, 1, 1, 0, 1),
+    (2, 32, 65, 33, 1, 5, 1, 1, 1, 2, 0),
+    (2, 96, 40, 100, 1, 1, 11, 1, 1, 0, 5),
+    (1, 32, 100, 40, 1, 11, 1, 1, 1, 5, 0),
+    (2, 32, 5, 3, 1, 1, 21, 1, 1, 0, 10),
+    (2, 32, 3, 5, 1, 7, 1, 1, 1, 3, 0),
 ]
 
 
@@ -133,6 +142,23 @@ def test_dwconv_vs_torch(B, case, dt):
     y2 = B.dwconv(B.to_nhwc(x.cuda()), wpk, b.float().cuda(), mult, kh, kw, (sh, sw), (ph, pw),
                   res=res.to(dt).float().cuda(), add=B.to_nhwc(add.cuda()).contiguous())
     assert O.compare4d(ref2.float(), nchw(y2)) < (tol if dt == torch.float32 else 3e-3)
+
+
+@pytest.mark.parametrize("k,along_w", [(3, True), (7, True), (7, False), (11, False), (21, True), (21, False)])
+def test_tma_strip_kernel_is_bit_identical_to_the_register_window_kernel(B, k, along_w, monkeypatch):
+    """The TMA-fed strip kernel (csrc/dwstrip_tma.cu) accumulates the taps in the same order as dw_strip_kernel, so the two agree
+    bit for bit; CNA_DW_NO_TMA selects the old one.  Shape with ragged tiles on both axes and three channel chunks."""
+    torch.manual_seed(k)
+    kh, kw = (1, k) if along_w else (k, 1)
+    x = torch.randn(3, 45, 77, 96, device="cuda").bfloat16()
+    w = torch.randn(96, 1, kh, kw, device="cuda") / k ** 0.5
+    wpk = B.pack_dw(w, torch.bfloat16)
+    b = torch.randn(96, device="cuda")
+    y_new = B.dwconv(x, wpk, b, 1, kh, kw, (1, 1), (kh // 2, kw // 2))
+    monkeypatch.setenv("CNA_DW_NO_TMA", "1")
+    y_old = B.dwconv(x, wpk, b, 1, kh, kw, (1, 1), (kh // 2, kw // 2))
+    monkeypatch.delenv("CNA_DW_NO_TMA")
+    assert torch.equal(y_new, y_old)
 
 
 @pytest.mark.parametrize("H", [24, 7, 20])

@@ -54,7 +54,7 @@ def measure_write_peak(dev, nbytes=1644167168, iters=10):
     L2), timed with CUDA events.  MEASURED_PEAKS.json's figure is a COPY (half reads, half writes); the write direction alone
     stops at ~60 % of it (profiles/r02_hbm_write_peak.txt), which is what bounds a layer that writes 4x what it reads."""
     buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    ms = _time_cuda(lambda: buf.zero_(), iters, warmup=3)
+    ms = min(_time_cuda(lambda: buf.zero_(), iters, warmup=3) for _ in range(3))     # a peak: best of three timed runs
     del buf
     return nbytes / ms / 1e6
 

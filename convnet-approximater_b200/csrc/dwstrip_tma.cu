@@ -250,6 +250,9 @@ static int strip_tma_launch(const void* x, const void* w, const float* bias, voi
 int dw_strip_tma_try(const void* x, const void* w, const float* bias, void* y, int B, int H, int W, int C, int kh, int kw, cudaStream_t st) {
     if (C % kSC != 0 || getenv("CNA_DW_NO_TMA") != nullptr) return -1;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15u) return -1;
+    // a strip axis of <= 16 positions leaves half of every 32-long tile empty: the register-window kernel is faster there
+    // (16 x 16 images at C = 256: 0.47 against 0.38 of the HBM peak, profiles/r02_strip_tma.txt)
+    if ((kh == 1 ? W : H) <= 16 && getenv("CNA_DW_FORCE_TMA") == nullptr) return -1;
     static const bool wide = getenv("CNA_STRIP_LINES16") != nullptr;      // diagnostic: the 16-line, one-CTA-per-SM configuration
 #define CNA_STRIP_TMA_CASE(KV) \
     if (kh == 1 && kw == KV) return wide ? strip_tma_launch<KV, true, 16>(x, w, bias, y, B, H, W, C, st) : strip_tma_launch<KV, true, 8>(x, w, bias, y, B, H, W, C, st); \

@@ -117,8 +117,8 @@ DW_CASES = [
     (2, 32, 65, 33, 1, 5, 1, 1, 1, 2, 0),
     (2, 96, 40, 100, 1, 1, 11, 1, 1, 0, 5),
     (1, 32, 100, 40, 1, 11, 1, 1, 1, 5, 0),
-    (2, 32, 5, 3, 1, 1, 21, 1, 1, 0, 10),
-    (2, 32, 3, 5, 1, 7, 1, 1, 1, 3, 0),
+    (2, 32, 5, 19, 1, 1, 21, 1, 1, 0, 10),
+    (2, 32, 19, 5, 1, 7, 1, 1, 1, 3, 0),
 ]
 
 

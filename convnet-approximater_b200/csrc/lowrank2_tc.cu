@@ -71,7 +71,7 @@ struct LR2Params {
     int ntiles;
     int stages;            // x (+Wv) ring depth
     int hslots;            // Wh ring depth (streamed mode)
-    int resident;          // 1: all weights stay in smem for the whole kernel; 0: streamed per tile
+    int res_v, res_h;      // Wv / Wh stay in smem for the whole kernel (1) or are streamed per tile (0): Wv with its x chunk, Wh through its ring
     int relu;
     int pool;              // fuse a 2x2/stride-2 max-pool into the epilogue (y is then [B, H/2, W/2, N])
     // smem byte offsets from the 1024-aligned base
@@ -250,11 +250,12 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             constexpr uint32_t x_bytes = kXRows * kTileCols * XROW;
             constexpr uint32_t v_bytes = 3 * KP * XROW;
             constexpr uint32_t h_bytes = NT2 * HROW;
-            if (p.resident && elect_one()) {
-                mbar_arrive_expect_tx(bar(BAR_WFULL), v_bytes * p.nch + (p.t_only ? 0u : h_bytes * 3 * p.nn2));
-                for (int ch = 0; ch < p.nch; ++ch)
+            if ((p.res_v || p.res_h) && elect_one()) {
+                const bool rh = p.res_h && !p.t_only;
+                mbar_arrive_expect_tx(bar(BAR_WFULL), (p.res_v ? v_bytes * p.nch : 0u) + (rh ? h_bytes * 3 * p.nn2 : 0u));
+                for (int ch = 0; ch < (p.res_v ? p.nch : 0); ++ch)
                     tma_load_2d(base + p.off_v + ch * p.v_chunk, &tm_wv, bar(BAR_WFULL), ch * CK, 0);
-                for (int n2 = 0; n2 < (p.t_only ? 0 : p.nn2); ++n2)
+                for (int n2 = 0; n2 < (rh ? p.nn2 : 0); ++n2)
                     for (int dx = 0; dx < 3; ++dx)
                         tma_load_2d(base + p.off_h + (n2 * 3 + dx) * p.h_slot, &tm_wh, bar(BAR_WFULL), 0, dx * p.N + n2 * NT2);
             }
@@ -266,9 +267,9 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                     if ((p.debug & 16) && it * p.nch + ch >= p.stages) continue;
                     mbar_wait(bar(BAR_XEMPTY + xs), xph ^ 1u);
                     if (elect_one()) {
-                        mbar_arrive_expect_tx(bar(BAR_XFULL + xs), x_bytes + (p.resident ? 0u : v_bytes));
+                        mbar_arrive_expect_tx(bar(BAR_XFULL + xs), x_bytes + (p.res_v ? 0u : v_bytes));
                         tma_load_4d(base + p.off_x + xs * p.x_stage, &tm_x, bar(BAR_XFULL + xs), ch * CK, t.w0 - 1, t.h0 - 1, t.b);
-                        if (!p.resident)
+                        if (!p.res_v)
                             tma_load_2d(base + p.off_v + xs * p.v_chunk, &tm_wv, bar(BAR_XFULL + xs), ch * CK, 0);
                     }
                     __syncwarp();
@@ -277,7 +278,7 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 if (lane == 0) stamp(it, 0);
             }
         }
-    } else if (warp == 15 && !p.resident && !p.t_only) {
+    } else if (warp == 15 && !p.res_h && !p.t_only) {
         // =========================== Wh TMA producer (streamed weights only) ===========================
         if (my_tiles > 0) {
             constexpr uint32_t h_bytes = NT2 * HROW;
@@ -300,7 +301,7 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             constexpr uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KP >> 3) << 17) | (8u << 24);
             constexpr uint64_t xdesc = desc_hi(16, 8 * XROW, swz_type(XROW));     // x tile and Wv chunk (swizzled, K-major)
             int xs = 0; uint32_t xph = 0;
-            if (p.resident) { mbar_wait(bar(BAR_WFULL), 0); tc_fence_after_sync(); }
+            if (p.res_v) { mbar_wait(bar(BAR_WFULL), 0); tc_fence_after_sync(); }
             for (int it = 0; it < my_tiles; ++it) {
                 const int buf = it & 1;          // barrier pair of this tile (its T-epilogue group)
                 if (lane == 0) stamp(it, 1);
@@ -317,7 +318,7 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                     tc_fence_after_sync();
                     if (lane == 0 && ch == 0) stamp(it, 2);
                     const uint64_t a0 = xdesc + ((base + p.off_x + xs * p.x_stage) >> 4);
-                    const uint64_t b0 = xdesc + ((base + p.off_v + (p.resident ? ch : xs) * p.v_chunk) >> 4);
+                    const uint64_t b0 = xdesc + ((base + p.off_v + (p.res_v ? ch : xs) * p.v_chunk) >> 4);
                     if (elect_one()) {
                         if (!(p.debug & 128))
 #pragma unroll
@@ -337,19 +338,19 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         }
     } else if (p.t_only && (warp == 10 || warp == 15)) {
         // 3-tap convolution only: no GEMM2
-    } else if (warp == 10 || (warp == 15 && p.resident && p.nn2 == 1)) {
+    } else if (warp == 10 || (warp == 15 && p.res_h && p.nn2 == 1)) {
         // =========================== GEMM2 issuer (A = bf16 T in TMEM, B = Wh tap slot in smem) ===========================
         // With resident weights and a single N-tile per tile (the 64-channel layers) the even and the odd tiles form two
         // independent pipelines (own T accumulator, A buffer, Y accumulator, epilogue groups), so they also get an issuing
         // warp each — warp 10 and the otherwise idle Wh producer warp 15: the per-tile barrier latencies of one issuer
         // (~750 cycles) then overlap the other's MMAs instead of idling the tensor pipe.
-        const bool split = p.resident && p.nn2 == 1;
+        const bool split = p.res_h && p.nn2 == 1;
         const int j0 = split ? (warp == 15 ? 1 : 0) : 0, jstep = split ? 2 : 1;
         if (my_tiles > 0) {
             constexpr uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT2 >> 3) << 17) | (8u << 24);
             constexpr uint64_t hdesc = desc_hi(16, 8 * HROW, swz_type(HROW));
             int hs = 0; uint32_t hph = 0;    // Wh ring
-            if (p.resident) { mbar_wait(bar(BAR_WFULL), 0); tc_fence_after_sync(); }
+            if (p.res_h) { mbar_wait(bar(BAR_WFULL), 0); tc_fence_after_sync(); }
             for (int j = j0; j < my_tiles; j += jstep) {
                 if (lane == 0) stamp(j, 4);
                 const int ab = j & 1;
@@ -371,7 +372,7 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                     }
                     if (lane == 0 && n2 == 0) stamp(j, 16);
                     const uint32_t d = tmem_Y + yb * NT2;
-                    if (p.resident) {
+                    if (p.res_h) {
                         const uint64_t b0 = hdesc + ((base + p.off_h + n2 * 3 * p.h_slot) >> 4);
                         const uint32_t slot16 = p.h_slot >> 4;
                         if (elect_one()) {
@@ -676,42 +677,57 @@ static int pick_ck(int c_pad) { return c_pad % 64 == 0 ? 64 : (c_pad % 32 == 0 ?
 static int pick_nt2(int N) { return N % 128 == 0 ? 128 : 64; }
 static uint32_t up1k(uint32_t v) { return (v + 1023u) & ~1023u; }
 
-// Fills the smem plan for `ystg` store buffers per epilogue group; returns total dynamic smem bytes (incl. 1 KB alignment slack)
-// or 0 if it cannot fit.
-static size_t plan_smem_ystg(LR2Params& p, int CK, int KP, int NT2, size_t limit, int ystg) {
+// Fills the smem plan for `ystg` store buffers per epilogue group and the residency mode (rv, rh) = (Wv resident, Wh resident);
+// returns total dynamic smem bytes (incl. 1 KB alignment slack) or 0 if it cannot fit.  A streamed Wv chunk travels with its x chunk
+// (same ring stage), streamed Wh taps go through their own ring of `hslots` slots.
+static size_t plan_smem_mode(LR2Params& p, int CK, int KP, int NT2, size_t limit, int ystg, int rv, int rh, int min_stages) {
     const uint32_t pool_bytes = p.pool ? 2 * ystg * 4096 : 0;
     const uint32_t ybytes = up1k((p.pool ? 2 : 2 * ystg) * kYBuf);
     const uint32_t xrow = CK * 2, hrow = KP * 2;
-    p.nystg = ystg;
+    p.nystg = ystg; p.res_v = rv; p.res_h = rh;
     p.x_stage = up1k(kXRows * kTileCols * xrow);
     p.v_chunk = up1k(3 * KP * xrow);
     p.h_slot = up1k(NT2 * hrow);
-    const uint32_t fixed = ybytes + pool_bytes + up1k(p.N * 4) + 1024 /*barriers*/ + 1024 /*align slack*/;
-    auto layout = [&](int resident, int stages, int hslots) {
-        p.resident = resident; p.stages = stages; p.hslots = hslots;
+    const size_t fixed = (size_t)ybytes + pool_bytes + up1k(p.N * 4) + 1024 /*barriers*/ + 1024 /*align slack*/ +
+                         (rv ? (size_t)p.nch * p.v_chunk : 0) + (rh ? (size_t)3 * p.nn2 * p.h_slot : 0);
+    const size_t per_stage = (size_t)p.x_stage + (rv ? 0 : p.v_chunk);
+    for (int stages = kMaxStages; stages >= min_stages; --stages) {
+        const size_t used = fixed + (size_t)stages * per_stage;
+        if (used + (rh ? 0 : 3 * (size_t)p.h_slot) > limit) continue;
+        const int hslots = rh ? 0 : (int)std::min<size_t>(kMaxHSlots, (limit - used) / p.h_slot);
+        p.stages = stages; p.hslots = hslots;
         uint32_t o = 0;
         p.off_x = o; o += stages * p.x_stage;
-        p.off_v = o; o += (resident ? p.nch : stages) * p.v_chunk;
-        p.off_h = o; o += (resident ? 3 * p.nn2 : hslots) * p.h_slot;
+        p.off_v = o; o += (rv ? p.nch : stages) * p.v_chunk;
+        p.off_h = o; o += (rh ? 3 * p.nn2 : hslots) * p.h_slot;
         p.off_y = o; o += ybytes;
         p.off_p = o; o += pool_bytes;
         p.off_bias = o; o += up1k(p.N * 4);
         p.off_bar = o;
         return (size_t)o + 2048;
-    };
-    // all weights resident, x ring at least 3 deep
-    for (int stages = kMaxStages; stages >= 3; --stages) {
-        size_t total = (size_t)fixed + (size_t)stages * p.x_stage + (size_t)p.nch * p.v_chunk + (size_t)3 * p.nn2 * p.h_slot;
-        if (total <= limit) return layout(1, stages, 0);
-    }
-    // streamed: Wv chunk travels with its x chunk, Wh through its own ring of tap slots
-    for (int stages = kMaxStages; stages >= 2; --stages) {
-        size_t used = (size_t)fixed + (size_t)stages * (p.x_stage + p.v_chunk);
-        if (used + 3 * (size_t)p.h_slot > limit) continue;
-        int hslots = (int)std::min<size_t>(kMaxHSlots, (limit - used) / p.h_slot);
-        return layout(0, stages, hslots);
     }
     return 0;
+}
+
+// Residency: everything resident when it fits next to an x ring of >= 3 stages (the 64- and 128-channel layers).  Otherwise one of
+// Wv / Wh may stay resident while the other streams - measured per VGG layer on one box (profiles/r02_fused_conv_residency.txt): it pays
+// where the x ring still holds a whole tile (<= 2 channel chunks: 128 -> 256 @56, -5 %) or where Wh is the bulk of the traffic
+// (>= 4 N-tiles: 256 -> 512 @28, -8 %), and costs 15 % on 256 -> 256 @56, whose rings shrink to 2 stages / 3 slots.
+// CNA_LR2_MODE=<rv><rh> (e.g. 01) forces a mode wherever it fits (diagnostic sweeps).
+static size_t plan_smem_ystg(LR2Params& p, int CK, int KP, int NT2, size_t limit, int ystg) {
+    static const int forced = [] { const char* e = getenv("CNA_LR2_MODE"); return (e && e[0] && e[1]) ? ((e[0] - '0') * 2 + (e[1] - '0')) : -1; }();
+    if (forced >= 0) {
+        size_t s = plan_smem_mode(p, CK, KP, NT2, limit, ystg, forced >> 1, forced & 1, 2);
+        if (s) return s;
+    }
+    if (size_t s = plan_smem_mode(p, CK, KP, NT2, limit, ystg, 1, 1, 3)) return s;
+    if (p.nch <= 2 || p.nn2 >= 4) {
+        const size_t v_all = (size_t)p.nch * up1k(3 * KP * CK * 2), h_all = (size_t)3 * p.nn2 * up1k(NT2 * KP * 2);
+        const int first_v = v_all >= h_all ? 1 : 0;          // try to keep the larger operand resident first
+        if (size_t s = plan_smem_mode(p, CK, KP, NT2, limit, ystg, first_v, 1 - first_v, 2)) return s;
+        if (size_t s = plan_smem_mode(p, CK, KP, NT2, limit, ystg, 1 - first_v, first_v, 2)) return s;
+    }
+    return plan_smem_mode(p, CK, KP, NT2, limit, ystg, 0, 0, 2);
 }
 
 // Store-buffer depth: the deepest (<= kAutoYStg) that costs the plan neither its resident weights nor an x stage nor Wh slots below
@@ -729,7 +745,8 @@ static size_t plan_smem(LR2Params& p, int CK, int KP, int NT2, size_t limit) {
     for (int y = kAutoYStg; y >= 2; --y) {
         LR2Params q = p;
         size_t s = plan_smem_ystg(q, CK, KP, NT2, limit, y);
-        if (s && q.resident == base.resident && q.stages >= base.stages && (q.resident || q.hslots >= std::min(base.hslots, 3 * p.nn2))) { p = q; return s; }
+        if (s && q.res_v == base.res_v && q.res_h == base.res_h && q.stages >= base.stages &&
+            (q.res_h || q.hslots >= std::min(base.hslots, 3 * p.nn2))) { p = q; return s; }
     }
     p = base;
     return s1;
@@ -812,6 +829,9 @@ static int lr2_launch(const void* x, const void* wv_packed, const void* wh_packe
     p.ntiles = (int)ntiles;
     size_t smem = plan_smem(p, CK, k_pad, NT2, (size_t)max_smem);
     CNA_CHECK(smem != 0, "shared-memory plan does not fit");
+    if (getenv("CNA_LR2_VERBOSE") != nullptr)
+        fprintf(stderr, "lowrank2 plan: C=%d K=%d N=%d H=%d W=%d pool=%d | CK=%d NT2=%d Wv %s Wh %s x-stages=%d hslots=%d ystg=%d smem=%zu\n", c_pad, k_pad,
+                N, H, W, pool, CK, NT2, p.res_v ? "resident" : "streamed", p.res_h ? "resident" : "streamed", p.stages, p.hslots, p.nystg, smem);
 
     CUtensorMap tm_x, tm_wv, tm_wh, tm_y;
     {

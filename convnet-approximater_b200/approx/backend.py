@@ -29,6 +29,8 @@ _SIGS = {
     "cna_pack_dw_weight": "ppiiiip",
     "cna_conv_taps_forward": "pppppiiiiiiiiiiiip",
     "cna_dwconv_forward": "ppppippiiiiiiiiiiiip",
+    "cna_dwconv3x3_act_forward": "ppppiiiiip",
+    "cna_conv1x1_tc_forward_strided": "pLpLppppppLLiiiip",
     "cna_conv1x1_tc_supported": "ii",
     "cna_conv1x1_pack": "ppiip",
     "cna_conv1x1_tc_forward": "pppppLiiip",
@@ -301,6 +303,30 @@ def conv1x1_tc_ex(x, w_nc, bias, act="none", residual=None, alpha=None, beta=Non
     return y
 
 
+def conv1x1_tc_slab(a2d, k0, kc, w_nc, n0, nc, bias, y2d, act="none", aux2d=None, alpha=None, beta=None, delta=None):
+    """One slab of a 1x1 conv on the tcgen05 kernel: y2d[:, n0:n0+nc] = epilogue(a2d[:, k0:k0+kc] . w_nc[n0:n0+nc, k0:k0+kc]^T + bias) with
+    the epilogues of conv1x1_tc_ex; a2d (P, Ca), w_nc (N, Ca), y2d / aux2d (P, Ny) bf16 row-major (aux2d may be y2d: in-place
+    accumulation over K slabs).  bias / alpha / beta / delta are fp32 vectors of nc elements (already sliced) or None."""
+    _ready(a2d)
+    P, Ca = a2d.shape
+    N, Cw = w_nc.shape
+    Ny = y2d.shape[1]
+    assert a2d.dtype == torch.bfloat16 and w_nc.dtype == torch.bfloat16 and y2d.dtype == torch.bfloat16
+    assert a2d.is_contiguous() and w_nc.is_contiguous() and y2d.is_contiguous() and y2d.shape[0] == P and Cw == Ca
+    assert 0 <= k0 and k0 + kc <= Ca and 0 <= n0 and n0 + nc <= N and n0 + nc <= Ny
+    for v in (bias, alpha, beta, delta):
+        assert v is None or (v.dtype == torch.float32 and v.numel() == nc and v.is_contiguous())
+    if aux2d is not None:
+        assert aux2d.shape == y2d.shape and aux2d.dtype == y2d.dtype and aux2d.is_contiguous()
+    code = {"none": 0, "relu": 1, "gelu": 2}[act]
+    off = lambda t, e: t.data_ptr() + 2 * e
+    with torch.cuda.device(a2d.device):
+        _check(lib().cna_conv1x1_tc_forward_strided(off(a2d, k0), Ca, off(w_nc, n0 * Cw + k0), Cw, _p(bias), off(aux2d, n0) if aux2d is not None else 0,
+                                                    _p(alpha), _p(beta), _p(delta), off(y2d, n0), Ny, P, kc, nc, code, 1 if aux2d is not None else 0,
+                                                    _stream(a2d)))
+    return y2d
+
+
 def lowrank1_fused_supported(B, H, W, C, N, M, d, separable) -> bool:
     return bool(lib().cna_lowrank1_fused_supported(int(B), int(H), int(W), int(C), int(N), int(M), int(d), int(bool(separable))))
 
@@ -383,6 +409,18 @@ def dwconv(x, wpk, bias, mult, kh, kw, stride=(1, 1), pad=(0, 0), res=None, add=
     with torch.cuda.device(x.device):
         _check(lib().cna_dwconv_forward(_p(x), _p(wpk), _p(bias), _p(res), res_p, _p(add), _p(y), B, H, W, C, mult,
                                         kh, kw, sh, sw, ph, pw, dtype_code(x.dtype), _stream(x)))
+    return y
+
+
+def dwconv3x3_act(x, wpk, bias, act=None):
+    """Depthwise 3x3 ('same', stride 1) + bias + optional exact GELU in one pass: x (B,H,W,C) bf16 NHWC, wpk [9][C] bf16."""
+    _ready(x)
+    B, H, W, C = x.shape
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and wpk.shape == (9, C) and wpk.dtype == x.dtype
+    assert act in (None, "gelu")
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _check(lib().cna_dwconv3x3_act_forward(_p(x), _p(wpk), _p(bias), _p(y), B, H, W, C, 2 if act == "gelu" else 0, _stream(x)))
     return y
 
 

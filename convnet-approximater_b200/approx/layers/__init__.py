@@ -5,4 +5,5 @@ from .depth_seperable_conv import ParallelConv, CascadeConv, FixPaddingBias
 from .drop import DropPath
 from .msca import MSCA, MSCAProfile
 from .mscan_attention import MSCANAttention
+from .mscan_block import MSCANFFN, MSCANBlock
 from .dummy import DummyLayer

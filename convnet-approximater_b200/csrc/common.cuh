@@ -53,6 +53,9 @@ int dw_tile_try(const void* x, const void* w_packed, const float* bias, const fl
 // dwstrip_tma.cu: TMA-pipelined bf16 strips (1 x K / K x 1) without fused extras; 0 = launched, -1 = not taken, 1 = error
 int dw_strip_tma_try(const void* x, const void* w, const float* bias, void* y, int B, int H, int W, int C, int kh, int kw, cudaStream_t st);
 
+int dw_square_tma_try(const void* x, const void* w, const float* bias, void* y, int B, int H, int W, int C, int k, int gelu, int force,
+                      cudaStream_t st);
+
 // ---- per-device state ----------------------------------------------------------------------------
 // One process may drive several GPUs (one host thread per device or cudaSetDevice round-robin): SM count, the opt-in
 // shared-memory limit and every cudaFuncSetAttribute are per DEVICE, so nothing below is cached process-wide.

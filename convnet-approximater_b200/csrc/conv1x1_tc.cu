@@ -25,6 +25,7 @@ constexpr int kC1KC = 32;          // channels per K-chunk
 struct C1Params {
     long long P;       // pixels
     int C, N, nkc, ntiles, stages;
+    long long ldy;     // row stride (elements) of y and of the gate / residual tensor (N for dense tensors)
     int act;           // 0 none, 1 ReLU, 2 GELU (erf form, nn.GELU default)
     int aux_mode;      // what `gate` is: 0 multiplicative gate (y = bf16(v) * gate), 1 residual (y = alpha[n] v + beta[n] gate + delta[n])
     uint32_t off_a, a_stage, off_w, w_chunk, off_bias, off_bar;
@@ -156,7 +157,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                     if (n0 + q * 8 < c_hi) {      // volatile: the load is issued HERE, not sunk down to its first use
                         asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
                                      : "=r"(dst[q].x), "=r"(dst[q].y), "=r"(dst[q].z), "=r"(dst[q].w)
-                                     : "l"(reinterpret_cast<const uint4*>(gate + r * p.N + n0) + q));
+                                     : "l"(reinterpret_cast<const uint4*>(gate + r * p.ldy + n0) + q));
                     }
             }
         };
@@ -167,8 +168,8 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             mbar_wait(bar(C1_ACC_FULL + buf), (uint32_t)((it >> 1) & 1));
             tc_fence_after_sync();
             const bool ok = row < p.P;
-            const __nv_bfloat16* grow = gate ? gate + row * p.N : nullptr;
-            __nv_bfloat16* yrow = y + row * p.N;
+            const __nv_bfloat16* grow = gate ? gate + row * p.ldy : nullptr;
+            __nv_bfloat16* yrow = y + row * p.ldy;
             if (c_lo >= c_hi) {          // N = 16: group 1 owns no columns, but the accumulator barrier counts its threads
                 tc_fence_before_sync();
                 mbar_arrive(bar(C1_ACC_EMPTY + buf));
@@ -265,11 +266,12 @@ static EncodeTiledFn1 c1_get_encode() {
     return fn;
 }
 
-static int c1_encode2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer) {
+static int c1_encode2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer,
+                       uint64_t row_stride_elems = 0) {
     EncodeTiledFn1 fn = c1_get_encode();
     CNA_CHECK(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
     cuuint64_t dims[2] = {inner, outer};
-    cuuint64_t str[1] = {inner * 2};
+    cuuint64_t str[1] = {(row_stride_elems ? row_stride_elems : inner) * 2};
     cuuint32_t box[2] = {box_inner, box_outer};
     cuuint32_t es[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -301,6 +303,9 @@ int cna_conv1x1_pack(const float* w_nc, void* packed, int N, int C, void* stream
 int cna_conv1x1_tc_forward_ex(const void* a, const void* w_packed, const float* bias, const void* aux, const float* alpha,
                               const float* beta, const float* delta, void* y, long long P, int C, int N, int act, int aux_mode,
                               void* stream);
+int cna_conv1x1_tc_forward_strided(const void* a, long long lda, const void* w_packed, long long ldw, const float* bias, const void* aux,
+                                   const float* alpha, const float* beta, const float* delta, void* y, long long ldy, long long P, int C,
+                                   int N, int act, int aux_mode, void* stream);
 
 int cna_conv1x1_tc_forward(const void* a, const void* w_packed, const float* bias, const void* gate, void* y, long long P, int C,
                            int N, int relu, void* stream) {
@@ -310,7 +315,16 @@ int cna_conv1x1_tc_forward(const void* a, const void* w_packed, const float* bia
 int cna_conv1x1_tc_forward_ex(const void* a, const void* w_packed, const float* bias, const void* aux, const float* alpha,
                               const float* beta, const float* delta, void* y, long long P, int C, int N, int act, int aux_mode,
                               void* stream) {
+    return cna_conv1x1_tc_forward_strided(a, C, w_packed, C, bias, aux, alpha, beta, delta, y, N, P, C, N, act, aux_mode, stream);
+}
+
+int cna_conv1x1_tc_forward_strided(const void* a, long long lda, const void* w_packed, long long ldw, const float* bias, const void* aux,
+                                   const float* alpha, const float* beta, const float* delta, void* y, long long ldy, long long P, int C,
+                                   int N, int act, int aux_mode, void* stream) {
     const void* gate = aux;
+    CNA_CHECK(lda >= C && ldw >= C && ldy >= N && lda % 8 == 0 && ldw % 8 == 0 && ldy % 16 == 0, "bad leading dimensions (lda, ldw multiples of 8, ldy of 16)");
+    CNA_CHECK(((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(w_packed)) & 15u) == 0 &&
+              ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(aux)) & 31u) == 0, "operands must be 16-byte (a, w) / 32-byte (y, aux) aligned");
     CNA_CHECK(a && w_packed && y && P > 0, "bad arguments");
     CNA_CHECK(act >= 0 && act <= 2 && (aux_mode == 0 || aux_mode == 1), "bad epilogue selector");
     CNA_CHECK(aux_mode == 0 || aux != nullptr, "residual epilogue without a residual tensor");
@@ -322,7 +336,7 @@ int cna_conv1x1_tc_forward_ex(const void* a, const void* w_packed, const float* 
     static std::atomic<unsigned long long> attr_done{0};
     CNA_CUDA(ensure_dyn_smem(conv1x1_tc_kernel, max_smem, attr_done));
     C1Params p{};
-    p.P = P; p.C = C; p.N = N; p.nkc = C / kC1KC; p.act = act; p.aux_mode = aux_mode;
+    p.P = P; p.C = C; p.N = N; p.nkc = C / kC1KC; p.act = act; p.aux_mode = aux_mode; p.ldy = ldy;
     p.ntiles = (int)((P + 127) / 128);
     p.a_stage = 128 * 64;
     p.w_chunk = ((uint32_t)N * 64 + 1023u) & ~1023u;
@@ -335,8 +349,8 @@ int cna_conv1x1_tc_forward_ex(const void* a, const void* w_packed, const float* 
     p.off_a = 0; p.off_w = stages * p.a_stage; p.off_bias = p.off_w + wbytes; p.off_bar = p.off_bias + bias_bytes;
     const size_t smem = (size_t)p.off_bar + 2048;
     CUtensorMap tm_a, tm_w;
-    if (c1_encode2d(&tm_a, a, (uint64_t)C, (uint64_t)P, kC1KC, 128)) return 1;
-    if (c1_encode2d(&tm_w, w_packed, (uint64_t)C, (uint64_t)N, kC1KC, (uint32_t)N)) return 1;
+    if (c1_encode2d(&tm_a, a, (uint64_t)C, (uint64_t)P, kC1KC, 128, (uint64_t)lda)) return 1;
+    if (c1_encode2d(&tm_w, w_packed, (uint64_t)C, (uint64_t)N, kC1KC, (uint32_t)N, (uint64_t)ldw)) return 1;
     const int grid = std::min(p.ntiles, num_sms);
     conv1x1_tc_kernel<<<grid, kC1Threads, smem, as_stream(stream)>>>(tm_a, tm_w, bias, (const __nv_bfloat16*)gate, alpha, beta, delta,
                                                                      (__nv_bfloat16*)y, p);

@@ -334,6 +334,11 @@ static int dw_tile_dispatch(int kh, int kw, const void* x, const void* w, const 
         const int rc = dw_strip_tma_try(x, w, bias, y, B, H, W, C, kh, kw, st);      // TMA-fed shared-memory pipeline (dwstrip_tma.cu)
         if (rc >= 0) return rc;
     }
+    if (std::is_same<T, __nv_bfloat16>::value && res == nullptr && add == nullptr && kh == kw && (kh == 3 || kh == 5) &&
+        getenv("CNA_DW_NO_TMA_SQUARE") == nullptr) {
+        const int rc = dw_square_tma_try(x, w, bias, y, B, H, W, C, kh, 0, 0, st);       // same pipeline, 3 / 5 box rows per input column
+        if (rc >= 0) return rc;
+    }
     if (getenv("CNA_DW_NO_STRIP") == nullptr) {      // (diagnostic switch: use the smem-tiled kernel for strips too)
 #define CNA_STRIP_CASE(KV) \
         if (kh == 1 && kw == KV) { const int rc = dw_strip_launch_t<T, KV, true>(x, w, bias, res, res_p, add, y, B, H, W, C, st); if (rc >= 0) return rc; } \

@@ -74,16 +74,21 @@ __device__ __forceinline__ StripTile strip_decode(int tile, const StripParams& p
     return t;
 }
 
-template <int K, bool ALONG_W, int LINES>
+// K = taps along the axis a thread slides on, KX = taps across it (1 for the strips; 3 / 5 for the square 3x3 / 5x5 kernels, which
+// slide along W and read KX box rows per input column), GELU = exact erf-GELU on the fp32 sum before the rounding (the depthwise conv +
+// activation of MSCAN's FFN, reference models/mscan.py:58-59).
+template <int K, int KX, bool ALONG_W, int LINES, bool GELU>
 __global__ void __launch_bounds__(StripCfg<LINES>::kThreads, StripCfg<LINES>::kCtasPerSm)
 dw_strip_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y,
-                    const __nv_bfloat16* __restrict__ w /*[K][C]*/, const float* __restrict__ bias, const StripParams p) {
+                    const __nv_bfloat16* __restrict__ w /*[KH*KW][C]*/, const float* __restrict__ bias, const StripParams p) {
+    static_assert(KX == 1 || ALONG_W, "square kernels slide along W");
     using Cfg = StripCfg<LINES>;
     constexpr int kSLines = LINES;
     constexpr uint32_t kSOutBytes = Cfg::kOutBytes;
     constexpr int P = K / 2;
     constexpr int NIN = kSLong + K - 1;                          // input positions along the strip axis
-    constexpr int BW = ALONG_W ? (kSLong + K) : kSLines;          // box columns (1 x K: one spare column makes the count odd)
+    constexpr int PX = KX / 2;
+    constexpr int BW = ALONG_W ? (kSLong + K) : kSLines;          // box columns (sliding along W: one spare column makes the count odd)
     // byte strides inside a stage / the store buffer ([rows][cols][32 ch] bf16, dense = TMA box order)
     constexpr uint32_t kPix = kSC * 2;                            // 64 bytes per pixel
     constexpr uint32_t in_long = ALONG_W ? kPix : BW * kPix;      // step along the strip axis
@@ -118,7 +123,7 @@ dw_strip_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
             if (elect_one()) {
                 mbar_arrive_expect_tx(full(s), p.stage_bytes);
                 const int w0 = ALONG_W ? t.tg * kSLong - P : t.tl * kSLines;
-                const int h0 = ALONG_W ? t.tl * kSLines : t.tg * kSLong - P;
+                const int h0 = ALONG_W ? t.tl * kSLines - PX : t.tg * kSLong - P;
                 tma_load_4d(in0 + s * p.stage_bytes, &tm_x, full(s), t.cc * kSC, w0, h0, t.b);
             }
             __syncwarp();
@@ -132,7 +137,7 @@ dw_strip_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
         const uint32_t out_thr = (uint32_t)line * out_line + (uint32_t)pair * 4u;
         int s = 0; uint32_t ph = 0;
         int cc_have = -1;
-        float2 wt[K];
+        float2 wt[KX * K];
         float2 bz = make_float2(0.f, 0.f);
         for (int it = 0; it < my_tiles; ++it) {
             const StripTile t = strip_decode(first + it * step, p);
@@ -140,7 +145,7 @@ dw_strip_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                 cc_have = t.cc;
                 const int c = t.cc * kSC + pair * 2;
 #pragma unroll
-                for (int k = 0; k < K; ++k) wt[k] = s_unpack(__ldg(reinterpret_cast<const uint32_t*>(w + (size_t)k * p.C + c)));
+                for (int k = 0; k < KX * K; ++k) wt[k] = s_unpack(__ldg(reinterpret_cast<const uint32_t*>(w + (size_t)k * p.C + c)));
                 if (bias) bz = __ldg(reinterpret_cast<const float2*>(bias + c));
             }
             const uint32_t ob = out0 + (uint32_t)(it & 1) * kSOutBytes;
@@ -154,14 +159,21 @@ dw_strip_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
             for (int k = 0; k < K; ++k) acc[k] = bz;
 #pragma unroll
             for (int i = 0; i < NIN; ++i) {
-                const float2 xv = s_unpack(s_lds(src + (uint32_t)i * in_long));
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const int o = i - k;                          // output fed by tap k of input i
-                    if (o >= 0 && o < kSLong) acc[o % K] = s_ffma2(xv, wt[k], acc[o % K]);
+                for (int rx = 0; rx < KX; ++rx) {                 // the KX box rows this line's window covers
+                    const float2 xv = s_unpack(s_lds(src + (uint32_t)rx * in_line + (uint32_t)i * in_long));
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const int o = i - k;                      // output fed by tap (rx, k) of input i
+                        if (o >= 0 && o < kSLong) acc[o % K] = s_ffma2(xv, wt[rx * K + k], acc[o % K]);
+                    }
                 }
                 if (i >= K - 1) {                                 // output i-K+1 has all its taps
                     const int o = i - (K - 1);
+                    if constexpr (GELU) {
+                        acc[o % K].x = 0.5f * acc[o % K].x * (1.f + erff(acc[o % K].x * 0.70710678118654752f));
+                        acc[o % K].y = 0.5f * acc[o % K].y * (1.f + erff(acc[o % K].y * 0.70710678118654752f));
+                    }
                     __nv_bfloat162 r = __floats2bfloat162_rn(acc[o % K].x, acc[o % K].y);
                     s_sts(ob + out_thr + (uint32_t)o * out_long, *reinterpret_cast<uint32_t*>(&r));
                     acc[o % K] = bz;
@@ -211,7 +223,7 @@ static int strip_encode(CUtensorMap* m, const void* ptr, int B, int H, int W, in
     return 0;
 }
 
-template <int K, bool ALONG_W, int LINES>
+template <int K, int KX, bool ALONG_W, int LINES, bool GELU>
 static int strip_tma_launch(const void* x, const void* w, const float* bias, void* y, int B, int H, int W, int C, cudaStream_t st) {
     DevInfo di;
     if (dev_info(&di)) return 1;
@@ -226,7 +238,7 @@ static int strip_tma_launch(const void* x, const void* w, const float* bias, voi
     const long long ntiles = (long long)B * p.t_long * p.t_lines * p.n_cc;
     if (ntiles >= (1LL << 31)) return -1;
     p.ntiles = (int)ntiles;
-    const uint32_t box_w = ALONG_W ? kSLong + K : kSLines, box_h = ALONG_W ? kSLines : kSLong + K - 1;
+    const uint32_t box_w = ALONG_W ? kSLong + K : kSLines, box_h = ALONG_W ? kSLines + KX - 1 : kSLong + K - 1;
     p.stage_bytes = (box_w * box_h * kSC * 2 + 127u) & ~127u;
     const size_t fixed = 2 * (size_t)kSOutBytes + 1024 /*barriers*/ + 1024 /*alignment slack*/;
     const size_t budget = Cfg::kCtasPerSm == 1 ? (size_t)di.max_smem : ((size_t)di.max_smem - 2048) / 2;   // 1 KB per CTA is reserved by the system
@@ -236,13 +248,24 @@ static int strip_tma_launch(const void* x, const void* w, const float* bias, voi
     CUtensorMap tm_x, tm_y;
     if (strip_encode(&tm_x, x, B, H, W, C, box_w, box_h)) return 1;
     if (strip_encode(&tm_y, y, B, H, W, C, ALONG_W ? kSLong : kSLines, ALONG_W ? kSLines : kSLong)) return 1;
-    auto kern = dw_strip_tma_kernel<K, ALONG_W, LINES>;
+    auto kern = dw_strip_tma_kernel<K, KX, ALONG_W, LINES, GELU>;
     static std::atomic<unsigned long long> attr_done{0};
     CNA_CUDA(ensure_dyn_smem(kern, di.max_smem, attr_done));
     const int grid = std::min(p.ntiles, di.num_sms * Cfg::kCtasPerSm);
     kern<<<grid, Cfg::kThreads, smem, st>>>(tm_x, tm_y, (const __nv_bfloat16*)w, bias, p);
     CNA_LAUNCH_CHECK();
     return 0;
+}
+
+// Square 3x3 / 5x5 depthwise kernels on the same pipeline, optionally with GELU.  Same return convention as dw_strip_tma_try.
+int dw_square_tma_try(const void* x, const void* w, const float* bias, void* y, int B, int H, int W, int C, int k, int gelu, int force,
+                      cudaStream_t st) {
+    if (C % kSC != 0 || getenv("CNA_DW_NO_TMA") != nullptr) return -1;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15u) return -1;
+    if (W <= 16 && !force && getenv("CNA_DW_FORCE_TMA") == nullptr) return -1;        // half-empty tiles: the smem-tiled kernel is faster (16 x 16 images)
+    if (k == 3) return gelu ? strip_tma_launch<3, 3, true, 8, true>(x, w, bias, y, B, H, W, C, st) : strip_tma_launch<3, 3, true, 8, false>(x, w, bias, y, B, H, W, C, st);
+    if (k == 5 && !gelu) return strip_tma_launch<5, 5, true, 8, false>(x, w, bias, y, B, H, W, C, st);
+    return -1;
 }
 
 // bf16 strips without fused extras.  Returns 0 when launched, -1 when this kernel does not take the configuration (the caller
@@ -255,8 +278,8 @@ int dw_strip_tma_try(const void* x, const void* w, const float* bias, void* y, i
     if ((kh == 1 ? W : H) <= 16 && getenv("CNA_DW_FORCE_TMA") == nullptr) return -1;
     static const bool wide = getenv("CNA_STRIP_LINES16") != nullptr;      // diagnostic: the 16-line, one-CTA-per-SM configuration
 #define CNA_STRIP_TMA_CASE(KV) \
-    if (kh == 1 && kw == KV) return wide ? strip_tma_launch<KV, true, 16>(x, w, bias, y, B, H, W, C, st) : strip_tma_launch<KV, true, 8>(x, w, bias, y, B, H, W, C, st); \
-    if (kw == 1 && kh == KV) return wide ? strip_tma_launch<KV, false, 16>(x, w, bias, y, B, H, W, C, st) : strip_tma_launch<KV, false, 8>(x, w, bias, y, B, H, W, C, st);
+    if (kh == 1 && kw == KV) return wide ? strip_tma_launch<KV, 1, true, 16, false>(x, w, bias, y, B, H, W, C, st) : strip_tma_launch<KV, 1, true, 8, false>(x, w, bias, y, B, H, W, C, st); \
+    if (kw == 1 && kh == KV) return wide ? strip_tma_launch<KV, 1, false, 16, false>(x, w, bias, y, B, H, W, C, st) : strip_tma_launch<KV, 1, false, 8, false>(x, w, bias, y, B, H, W, C, st);
     CNA_STRIP_TMA_CASE(3)
     CNA_STRIP_TMA_CASE(5)
     CNA_STRIP_TMA_CASE(7)
@@ -267,3 +290,18 @@ int dw_strip_tma_try(const void* x, const void* w, const float* bias, void* y, i
 }
 
 }  // namespace cna
+
+using namespace cna;
+
+extern "C" int cna_dwconv3x3_act_forward(const void* x, const void* w_packed, const float* bias, void* y, int B, int H, int W, int C, int act,
+                                         void* stream) {
+    CNA_CHECK(x && w_packed && y && B > 0 && H > 0 && W > 0, "bad arguments");
+    CNA_CHECK(act == 0 || act == 2, "activation must be 0 (none) or 2 (GELU)");
+    CNA_CHECK(C % kSC == 0, "needs C % 32 == 0");
+    const int rc = dw_square_tma_try(x, w_packed, bias, y, B, H, W, C, 3, act == 2, 1, as_stream(stream));
+    CNA_CHECK(rc >= 0, "configuration not taken by the TMA depthwise kernel (16-byte aligned tensors, C % 32 == 0)");
+    if (rc) return rc;
+    count_launch();
+    return 0;
+}
+

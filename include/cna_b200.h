@@ -88,6 +88,14 @@ int cna_conv1x1_tc_forward_ex(const void* a, const void* w_packed, const float* 
                               const float* beta, const float* delta, void* y, long long P, int C, int N, int act, int aux_mode,
                               void* stream);
 
+/* The same kernel on sub-matrices: a is [P][lda] with the C contracted channels at its start, w_packed [N][ldw], y and aux [P][ldy]
+ * (element strides; lda, ldw multiples of 8, ldy of 16; pointers may be offset into a wider tensor).  This is how the FFN of an MSCAN
+ * block (src/approx/models/mscan.py:27-62) runs on it: fc1 writes its hidden tensor in slabs of <= 256 output channels, fc2 contracts
+ * the hidden channels in slabs whose weight fits in shared memory, accumulating into y through the residual epilogue (aux = y). */
+int cna_conv1x1_tc_forward_strided(const void* a, long long lda, const void* w_packed, long long ldw, const float* bias, const void* aux,
+                                   const float* alpha, const float* beta, const float* delta, void* y, long long ldy, long long P, int C,
+                                   int N, int act, int aux_mode, void* stream);
+
 /* ---- fused scheme-1 low-rank convolution (tcgen05) --------------------------------------------- */
 /* y = d_conv(s_conv(x)) in ONE kernel for bf16 NHWC tensors, stride 1, 'same' padding: the (B, C*M, H, W) intermediate of
  * LowRankExpConvV1.forward (src/approx/layers/low_rank_conv.py:44-52; SeparableConv :17-25 after decomp()) is produced by CUDA
@@ -118,6 +126,12 @@ int cna_dwconv_forward(const void* x, const void* w_packed, const float* bias, c
                        const void* add, void* y,
                        int B, int H, int W, int Cin, int mult, int kh, int kw,
                        int stride_h, int stride_w, int pad_h, int pad_w, int dtype, void* stream);
+
+/* Depthwise 3x3 + bias + exact GELU in one pass (bf16 NHWC, stride 1, 'same' padding, C % 32 == 0) on the TMA-fed shared-memory
+ * pipeline of csrc/dwstrip_tma.cu: FFN.dconv followed by FFN.act of an MSCAN block (src/approx/models/mscan.py:38-45, 58-59).
+ * act: 0 = none, 2 = GELU.  w_packed [9][C] bf16 as for cna_dwconv_forward. */
+int cna_dwconv3x3_act_forward(const void* x, const void* w_packed, const float* bias, void* y, int B, int H, int W, int C, int act,
+                              void* stream);
 
 /* out = a + b elementwise over `count` elements (ParallelConv's identity branch). */
 int cna_add(const void* a, const void* b, void* out, long long count, int dtype, void* stream);

@@ -161,6 +161,24 @@ def test_tma_strip_kernel_is_bit_identical_to_the_register_window_kernel(B, k, a
     assert torch.equal(y_new, y_old)
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 37, 45), (1, 256, 16, 16), (3, 32, 70, 9)])
+@pytest.mark.parametrize("act", [None, "gelu"])
+def test_dwconv3x3_gelu_tma_vs_torch(B, shape, act):
+    """FFN.dconv + FFN.act of an MSCAN block (reference models/mscan.py:38-45, 58-59) in one pass; bf16 vs the fp32 math on the
+    same bf16 inputs, tolerance = one bf16 rounding of the output."""
+    Bn, C, H, W = shape
+    torch.manual_seed(7)
+    x = torch.randn(Bn, C, H, W).bfloat16()
+    w = (torch.randn(C, 1, 3, 3) / 3).bfloat16()
+    b = torch.randn(C).bfloat16()
+    ref = F.conv2d(x.float(), w.float(), b.float(), 1, 1, groups=C)
+    if act == "gelu":
+        ref = F.gelu(ref)
+    y = B.dwconv3x3_act(B.to_nhwc(x.cuda()).contiguous(), B.pack_dw(w.cuda().float(), torch.bfloat16), b.float().cuda(), act)
+    assert O.compare4d(ref, nchw(y)) < 3e-3
+    assert O.compare4d(ref.bfloat16().float(), nchw(y)) < TOL16
+
+
 @pytest.mark.parametrize("H", [24, 7, 20])
 def test_fix_padding_bias_inplace(B, H):
     torch.manual_seed(3)

@@ -260,6 +260,48 @@ def bench_msca(dev, peaks, batch=32, iters=10):
         del keep, graph
         out["attention_half_fused"] = {"ms_13_blocks": ms, "images_per_s": batch / ms * 1e3, "kernels_per_block": 4,
                                        "what": "x + layer_scale_1 * (proj_2(MSCA(gelu(proj_1(norm1(x))))) + norm1(x)), eval mode"}
+        # ---- the whole MSCAN block: attention half + FFN half (fc1 -> 3x3 depthwise -> GELU -> fc2; models/mscan.py:27-62, 108-112)
+        from approx.layers import MSCANBlock
+        exp = {32: 8, 64: 8, 160: 4, 256: 4}
+        full_blocks = []
+        hidden_bytes = 0
+        for (C, H, nblk) in MSCAN_T:
+            Hd = C * exp[C]
+
+            class Attn2(nn.Module):
+                def __init__(s_, C=C):
+                    super().__init__()
+                    s_.proj_1 = nn.Conv2d(C, C, 1)
+                    s_.spatial_gating_unit = MSCA(C, 5, (7, 11, 21))
+                    s_.proj_2 = nn.Conv2d(C, C, 1)
+
+            class FFN(nn.Module):
+                def __init__(s_, C=C, Hd=Hd):
+                    super().__init__()
+                    s_.fc1 = nn.Conv2d(C, Hd, 1)
+                    s_.dconv = nn.Conv2d(Hd, Hd, 3, 1, 1, groups=Hd)
+                    s_.fc2 = nn.Conv2d(Hd, C, 1)
+            blk = MSCANBlock(nn.BatchNorm2d(C), Attn2(), nn.Parameter(0.01 * torch.ones(C)), nn.BatchNorm2d(C), FFN(),
+                             nn.Parameter(0.01 * torch.ones(C))).to(dev).bfloat16().eval()
+            full_blocks += [(blk, torch.randn(batch, H, H, C, device=dev).bfloat16()) for _ in range(nblk)]
+            hidden_bytes += nblk * batch * H * H * Hd * 2
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.no_grad(), torch.cuda.stream(side):
+            for m, x in full_blocks:
+                m.forward_nhwc(x)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(graph):
+            keep = [m.forward_nhwc(x) for m, x in full_blocks]
+        ms_b = _time_cuda(graph.replay, iters)
+        del keep, graph, full_blocks
+        out["block_fused"] = {"ms_13_blocks": ms_b, "images_per_s": batch / ms_b * 1e3, "ffn_half_ms": ms_b - ms,
+                              "ffn_hidden_traffic": {"bytes": 4 * hidden_bytes, "achieved": 4 * hidden_bytes / max(ms_b - ms, 1e-6) / 1e6,
+                                                     "unit": "GB/s", "frac": 4 * hidden_bytes / max(ms_b - ms, 1e-6) / 1e6 / hbm,
+                                                     "what": "the hidden tensor written by fc1, read + written by the depthwise 3x3 + GELU pass, read by fc2"},
+                              "what": "attention half, then x1 + layer_scale_2 * fc2(gelu(dconv(fc1(norm2(x1))))), eval mode"}
     except Exception as e:  # noqa: BLE001
         out["attention_half_fused"] = {"error": repr(e)}
     return out

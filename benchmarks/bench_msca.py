@@ -65,6 +65,9 @@ def torch_msca(C):
     return M()
 
 
+EXP = {32: 8, 64: 8, 160: 4, 256: 4}      # MSCAN-T exp_ratios per stage width (reference models/mscan.py:141)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=32)
@@ -169,6 +172,50 @@ def main():
                               "min_traffic_GBps": 2 * elems * esz / ms / 1e6}))
             total["attention_half_fused"] = total.get("attention_half_fused", 0.0) + ms * nblk
             total["attention_half_torch_cudnn"] = total.get("attention_half_torch_cudnn", 0.0) + ms_t * nblk
+            # ---- the whole block: attention half + FFN half (fc1 -> 3x3 depthwise -> GELU -> fc2, models/mscan.py:27-62, 108-112)
+            from approx.layers import MSCANBlock
+            Hd = C * EXP[C]
+
+            class FFN(nn.Module):
+                def __init__(s_):
+                    super().__init__()
+                    s_.fc1 = nn.Conv2d(C, Hd, 1)
+                    s_.dconv = nn.Conv2d(Hd, Hd, 3, 1, 1, groups=Hd)
+                    s_.fc2 = nn.Conv2d(Hd, C, 1)
+
+            ffn = FFN()
+            full = MSCANBlock(nn.BatchNorm2d(C), Attn(), nn.Parameter(0.01 * torch.ones(C)), nn.BatchNorm2d(C), ffn,
+                              nn.Parameter(0.01 * torch.ones(C))).cuda().to(dt).eval()
+            with torch.no_grad():
+                n0 = B.launch_count()
+                full.forward_nhwc(xs[0])
+                launches = B.launch_count() - n0
+                full.forward_nhwc(xs[0])
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    full.forward_nhwc(xs[0])
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                with torch.cuda.graph(graph):
+                    keep = [full.forward_nhwc(xi) for xi in xs]
+                ms_b = time_cuda(graph.replay, args.iters) / len(xs)
+                del keep, graph
+                bn2 = nn.BatchNorm2d(C).cuda().to(dt).eval()
+                tf = FFN().cuda().to(dt).to(memory_format=torch.channels_last).eval()
+
+                def torch_full():
+                    x1 = torch_block()
+                    return x1 + ls * tf.fc2(torch.nn.functional.gelu(tf.dconv(tf.fc1(bn2(x1)))))
+                ms_tb = time_cuda(torch_full, args.iters)
+            hidden_bytes = args.batch * H * H * Hd * esz
+            print(json.dumps({"bench": "mscan_block", "dtype": args.dtype, "C": C, "hidden": Hd, "H": H, "batch": args.batch, "ms": ms_b,
+                              "ffn_half_ms": ms_b - ms, "torch_cudnn_ms": ms_tb, "speedup_over_torch": ms_tb / ms_b, "kernels": launches,
+                              "ffn_hbm_GBps_on_4_hidden_passes": 4 * hidden_bytes / max(ms_b - ms, 1e-6) / 1e6}))
+            total["block_fused"] = total.get("block_fused", 0.0) + ms_b * nblk
+            total["block_torch_cudnn"] = total.get("block_torch_cudnn", 0.0) + ms_tb * nblk
         if args.torch:
             tm = torch_msca(C).cuda().to(dt).to(memory_format=torch.channels_last).eval()
             xt = x.permute(0, 3, 1, 2)

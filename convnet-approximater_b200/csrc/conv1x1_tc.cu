@@ -203,7 +203,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                     for (int i = 0; i < 8; ++i) f[i] = fmaxf(__uint_as_float(v[q * 8 + i]) + sbias[n0 + q * 8 + i], lo);
                     if (p.act == 2) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) f[i] = 0.5f * f[i] * (1.f + erff(f[i] * 0.70710678118654752f));
+                        for (int i = 0; i < 8; ++i) f[i] = gelu_erf_fast(f[i]);
                     }
                     if (grow && p.aux_mode == 1) {
                         // residual epilogue: y = alpha[n] v + beta[n] res + delta[n] in fp32, one rounding

@@ -171,8 +171,8 @@ dw_strip_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                 if (i >= K - 1) {                                 // output i-K+1 has all its taps
                     const int o = i - (K - 1);
                     if constexpr (GELU) {
-                        acc[o % K].x = 0.5f * acc[o % K].x * (1.f + erff(acc[o % K].x * 0.70710678118654752f));
-                        acc[o % K].y = 0.5f * acc[o % K].y * (1.f + erff(acc[o % K].y * 0.70710678118654752f));
+                        acc[o % K].x = gelu_erf_fast(acc[o % K].x);
+                        acc[o % K].y = gelu_erf_fast(acc[o % K].y);
                     }
                     __nv_bfloat162 r = __floats2bfloat162_rn(acc[o % K].x, acc[o % K].y);
                     s_sts(ob + out_thr + (uint32_t)o * out_long, *reinterpret_cast<uint32_t*>(&r));

@@ -153,9 +153,26 @@ def sd_convs_train(sd, a):
     return s
 
 
+class _ToNHWC(torch.autograd.Function):
+    """NCHW-contiguous -> NHWC-contiguous through the library's transpose kernel; the gradient comes back as a channels_last view."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return B.to_nhwc(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.permute(0, 3, 1, 2)
+
+
+def _nhwc(x):
+    v = x.permute(0, 2, 3, 1)
+    return v if v.is_contiguous() else _ToNHWC.apply(x)      # channels_last input: a free view autograd already understands
+
+
 def msca_train_forward(msca, x):
     """x (B,C,H,W) -> x * channel_mix(sd_convs(conv0(x))) with a full autograd graph over this library's kernels."""
-    xn = x.permute(0, 2, 3, 1).contiguous()
+    xn = _nhwc(x)
     a0 = _dw(msca.conv0, xn)
     s = sd_convs_train(msca.sd_convs, a0)
     m = _Conv1x1.apply(s, msca.channel_mix.weight, msca.channel_mix.bias, msca.channel_mix)
@@ -166,7 +183,7 @@ def lowrank1_train_forward(layer, x):
     """LowRankExpConvV1 (scheme 1) with a full autograd graph: s_conv (grouped d x d conv with channel multiplier, or its
     separable d x 1 . 1 x d form after decomp()) then the 1x1 d_conv (reference layers/low_rank_conv.py:51-52)."""
     from .low_rank_conv import SeparableConv
-    xn = x.permute(0, 2, 3, 1).contiguous()
+    xn = _nhwc(x)
     if isinstance(layer.s_conv, SeparableConv):
         t = _dw(layer.s_conv.h_conv, _dw(layer.s_conv.v_conv, xn))
     else:

@@ -7,8 +7,8 @@ drop_path are identities):
 
 Here (bf16 NHWC):
 
-    h = x1 . W1'^T + b1'                  BatchNorm folded into fc1 (W1' = W1 diag(s), b1' = W1 o + b1), tcgen05 1x1 kernel, one launch per
-                                          slab of <= 256 hidden channels (cna_conv1x1_tc_forward_strided writes into the wide tensor)
+    h = x1 . W1'^T + b1'                  BatchNorm folded into fc1 (W1' = W1 diag(s), b1' = W1 o + b1), tcgen05 1x1 kernel, one launch
+                                          whose CTAs split into groups per slab of <= 256 hidden channels (cna_conv1x1_tc_forward_strided)
     g = gelu(dconv3x3(h) + bd)            one TMA-pipelined pass (cna_dwconv3x3_act_forward)
     y = ls2 (g . W2^T + b2) + x1          fc2 + layer scale + residual in the 1x1 kernel's affine epilogue; the hidden channels are
                                           contracted in slabs whose weight fits in shared memory, accumulating into y in place
@@ -81,9 +81,7 @@ class MSCANFFN(nn.Module):
         x2 = x.view(P, C)
         h = torch.empty((Bn, H, W, Hd), device=x.device, dtype=x.dtype)
         h2 = h.view(P, Hd)
-        for n0 in range(0, Hd, 256):
-            nc = min(256, Hd - n0)
-            B.conv1x1_tc_slab(x2, 0, C, w1p, n0, nc, b1[n0:n0 + nc], h2)
+        B.conv1x1_tc_slab(x2, 0, C, w1p, 0, Hd, b1, h2)          # one launch: the kernel grids over slabs of 256 hidden channels
         g = B.dwconv3x3_act(h, wd, bd, "gelu")
         g2 = g.view(P, Hd)
         y = torch.empty_like(x)

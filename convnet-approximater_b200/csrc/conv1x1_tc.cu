@@ -26,6 +26,8 @@ struct C1Params {
     long long P;       // pixels
     int C, N, nkc, ntiles, stages;
     long long ldy;     // row stride (elements) of y and of the gate / residual tensor (N for dense tensors)
+    int nslab, slab_n; // output channels split into nslab slabs of slab_n (the last may be narrower): CTA b works on slab b % nslab, so
+                       // a conv with N > 256 (fc1 of MSCAN's FFN) is ONE launch; p.N is the total then
     int act;           // 0 none, 1 ReLU, 2 GELU (erf form, nn.GELU default)
     int aux_mode;      // what `gate` is: 0 multiplicative gate (y = bf16(v) * gate), 1 residual (y = alpha[n] v + beta[n] gate + delta[n])
     uint32_t off_a, a_stage, off_w, w_chunk, off_bias, off_bar;
@@ -63,6 +65,15 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     float* sbias = reinterpret_cast<float*>(base_ptr + p.off_bias);
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + p.off_bar + 8 * C1_COUNT);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // this CTA's slab of output channels: everything below sees only its N columns
+    const int slab = (int)(blockIdx.x % (unsigned)p.nslab), n_off = slab * p.slab_n;
+    const int N = min(p.slab_n, p.N - n_off);
+    if (bias) bias += n_off;
+    if (alpha) alpha += n_off;
+    if (beta) beta += n_off;
+    if (delta) delta += n_off;
+    if (gate) gate += n_off;
+    y += n_off;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tm_a); prefetch_tmap(&tm_w);
@@ -72,26 +83,27 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc<512>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
-    for (int i = threadIdx.x; i < p.N; i += kC1Threads) {
+    for (int i = threadIdx.x; i < N; i += kC1Threads) {
         sbias[i] = bias ? bias[i] : 0.f;
         if (p.aux_mode == 1) {          // per-channel affine of the residual epilogue: [alpha | beta | delta] after the bias
-            sbias[p.N + i] = alpha ? alpha[i] : 1.f;
-            sbias[2 * p.N + i] = beta ? beta[i] : 1.f;
-            sbias[3 * p.N + i] = delta ? delta[i] : 0.f;
+            sbias[N + i] = alpha ? alpha[i] : 1.f;
+            sbias[2 * N + i] = beta ? beta[i] : 1.f;
+            sbias[3 * N + i] = delta ? delta[i] : 0.f;
         }
     }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
-    const int first = blockIdx.x, step = gridDim.x;
+    const int first = blockIdx.x / p.nslab, step = gridDim.x / p.nslab;       // the launcher makes the grid a multiple of nslab
     const int my_tiles = first < p.ntiles ? (p.ntiles - first + step - 1) / step : 0;
 
     if (warp == 0) {
         if (my_tiles > 0) {
             if (elect_one()) {
-                mbar_arrive_expect_tx(bar(C1_WFULL), (uint32_t)(p.N * 64 * p.nkc));
-                for (int kc = 0; kc < p.nkc; ++kc) tma_load_2d(base + p.off_w + kc * p.w_chunk, &tm_w, bar(C1_WFULL), kc * kC1KC, 0);
+                // the weight box is slab_n rows tall; rows past the tensor's N (narrow last slab) are zero-filled and still counted
+                mbar_arrive_expect_tx(bar(C1_WFULL), (uint32_t)(p.slab_n * 64 * p.nkc));
+                for (int kc = 0; kc < p.nkc; ++kc) tma_load_2d(base + p.off_w + kc * p.w_chunk, &tm_w, bar(C1_WFULL), kc * kC1KC, n_off);
             }
             __syncwarp();
             int s = 0; uint32_t ph = 0;
@@ -110,7 +122,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         }
     } else if (warp == 1) {
         if (my_tiles > 0) {
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | (8u << 24);
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
             constexpr uint64_t dsc = c1_desc_hi(16, 8 * 64, 4);      // 64-byte rows, 64B swizzle, K-major
             int s = 0; uint32_t ph = 0;
             mbar_wait(bar(C1_WFULL), 0);
@@ -144,8 +156,8 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         // Two epilogue groups (warps 2-5, 6-9) split the N columns of every tile: with K = C <= 256 the GEMM is a few hundred cycles
         // and ONE group's ld -> math -> 32-byte stores chain per 32 columns bounded the kernel (40 us for 100 MB at C = 32).
         const int eg = warp >= 6 ? 1 : 0;
-        const int half = ((p.N / 2 + 15) / 16) * 16;                  // columns of group 0, a multiple of 16
-        const int c_lo = eg ? half : 0, c_hi = eg ? p.N : half;
+        const int half = ((N / 2 + 15) / 16) * 16;                    // columns of group 0, a multiple of 16
+        const int c_lo = eg ? half : 0, c_hi = eg ? N : half;
         // gate rows are fetched one 32-column chunk AHEAD (next chunk of this tile, or the first chunk of the warp's next tile):
         // the global-load latency of a chunk would otherwise be exposed once per tile
         uint4 gq[4], gnext[4];
@@ -212,8 +224,8 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                         for (int i = 0; i < 4; ++i) {
                             const int n = n0 + q * 8 + 2 * i;
                             const float r0 = __uint_as_float(g4[i] << 16), r1 = __uint_as_float(g4[i] & 0xffff0000u);
-                            f[2 * i] = sbias[p.N + n] * f[2 * i] + sbias[2 * p.N + n] * r0 + sbias[3 * p.N + n];
-                            f[2 * i + 1] = sbias[p.N + n + 1] * f[2 * i + 1] + sbias[2 * p.N + n + 1] * r1 + sbias[3 * p.N + n + 1];
+                            f[2 * i] = sbias[N + n] * f[2 * i] + sbias[2 * N + n] * r0 + sbias[3 * N + n];
+                            f[2 * i + 1] = sbias[N + n + 1] * f[2 * i + 1] + sbias[2 * N + n + 1] * r1 + sbias[3 * N + n + 1];
                         }
                     } else if (grow) {
                         // the reference multiplies two materialised bf16 tensors: round the conv output first
@@ -328,7 +340,10 @@ int cna_conv1x1_tc_forward_strided(const void* a, long long lda, const void* w_p
     CNA_CHECK(a && w_packed && y && P > 0, "bad arguments");
     CNA_CHECK(act >= 0 && act <= 2 && (aux_mode == 0 || aux_mode == 1), "bad epilogue selector");
     CNA_CHECK(aux_mode == 0 || aux != nullptr, "residual epilogue without a residual tensor");
-    CNA_CHECK(cna_conv1x1_tc_supported(C, N), "configuration not supported (needs C%32==0, N%16==0, N<=256, W resident in smem)");
+    // N > 256: slabs of 256 output channels (two accumulators of 256 TMEM columns), one CTA group per slab in the same launch
+    const int slab_n = N > 256 ? 256 : N, nslab = (N + slab_n - 1) / slab_n;
+    CNA_CHECK(N % 16 == 0 && cna_conv1x1_tc_supported(C, slab_n),
+              "configuration not supported (needs C%32==0, N%16==0, a 256-channel slab of W resident in smem)");
     CNA_CHECK(P < (1LL << 31) * 128LL, "too many pixels");
     DevInfo di;
     if (dev_info(&di)) return 1;
@@ -336,12 +351,12 @@ int cna_conv1x1_tc_forward_strided(const void* a, long long lda, const void* w_p
     static std::atomic<unsigned long long> attr_done{0};
     CNA_CUDA(ensure_dyn_smem(conv1x1_tc_kernel, max_smem, attr_done));
     C1Params p{};
-    p.P = P; p.C = C; p.N = N; p.nkc = C / kC1KC; p.act = act; p.aux_mode = aux_mode; p.ldy = ldy;
+    p.P = P; p.C = C; p.N = N; p.nkc = C / kC1KC; p.act = act; p.aux_mode = aux_mode; p.ldy = ldy; p.nslab = nslab; p.slab_n = slab_n;
     p.ntiles = (int)((P + 127) / 128);
     p.a_stage = 128 * 64;
-    p.w_chunk = ((uint32_t)N * 64 + 1023u) & ~1023u;
+    p.w_chunk = ((uint32_t)slab_n * 64 + 1023u) & ~1023u;
     const uint32_t wbytes = p.w_chunk * p.nkc;
-    const uint32_t bias_bytes = ((uint32_t)N * 16 + 1023u) & ~1023u;      // bias | alpha | beta | delta
+    const uint32_t bias_bytes = ((uint32_t)slab_n * 16 + 1023u) & ~1023u;      // bias | alpha | beta | delta
     int stages = kC1Stages;
     while (stages > 2 && (size_t)wbytes + (size_t)stages * p.a_stage + bias_bytes + 2048 > (size_t)max_smem) --stages;
     CNA_CHECK((size_t)wbytes + (size_t)stages * p.a_stage + bias_bytes + 2048 <= (size_t)max_smem, "shared-memory plan does not fit");
@@ -350,8 +365,8 @@ int cna_conv1x1_tc_forward_strided(const void* a, long long lda, const void* w_p
     const size_t smem = (size_t)p.off_bar + 2048;
     CUtensorMap tm_a, tm_w;
     if (c1_encode2d(&tm_a, a, (uint64_t)C, (uint64_t)P, kC1KC, 128, (uint64_t)lda)) return 1;
-    if (c1_encode2d(&tm_w, w_packed, (uint64_t)C, (uint64_t)N, kC1KC, (uint32_t)N, (uint64_t)ldw)) return 1;
-    const int grid = std::min(p.ntiles, num_sms);
+    if (c1_encode2d(&tm_w, w_packed, (uint64_t)C, (uint64_t)N, kC1KC, (uint32_t)slab_n, (uint64_t)ldw)) return 1;
+    const int grid = std::max(1, std::min(p.ntiles, num_sms / nslab)) * nslab;
     conv1x1_tc_kernel<<<grid, kC1Threads, smem, as_stream(stream)>>>(tm_a, tm_w, bias, (const __nv_bfloat16*)gate, alpha, beta, delta,
                                                                      (__nv_bfloat16*)y, p);
     CNA_LAUNCH_OK();

@@ -90,8 +90,9 @@ int cna_conv1x1_tc_forward_ex(const void* a, const void* w_packed, const float* 
 
 /* The same kernel on sub-matrices: a is [P][lda] with the C contracted channels at its start, w_packed [N][ldw], y and aux [P][ldy]
  * (element strides; lda, ldw multiples of 8, ldy of 16; pointers may be offset into a wider tensor).  This is how the FFN of an MSCAN
- * block (src/approx/models/mscan.py:27-62) runs on it: fc1 writes its hidden tensor in slabs of <= 256 output channels, fc2 contracts
- * the hidden channels in slabs whose weight fits in shared memory, accumulating into y through the residual epilogue (aux = y). */
+ * block (src/approx/models/mscan.py:27-62) runs on it: fc1 (N = hidden > 256 allowed here: the launch's CTAs split into groups per
+ * slab of 256 output channels), fc2 contracts the hidden channels in slabs whose weight fits in shared memory, accumulating into y
+ * through the residual epilogue (aux = y). */
 int cna_conv1x1_tc_forward_strided(const void* a, long long lda, const void* w_packed, long long ldw, const float* bias, const void* aux,
                                    const float* alpha, const float* beta, const float* delta, void* y, long long ldy, long long P, int C,
                                    int N, int act, int aux_mode, void* stream);

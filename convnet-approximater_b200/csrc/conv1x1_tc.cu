@@ -215,7 +215,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                     for (int i = 0; i < 8; ++i) f[i] = fmaxf(__uint_as_float(v[q * 8 + i]) + sbias[n0 + q * 8 + i], lo);
                     if (p.act == 2) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) f[i] = gelu_erf_fast(f[i]);
+                        for (int i = 0; i < 8; i += 2) { const float2 g2 = gelu_erf_fast2(f[i], f[i + 1]); f[i] = g2.x; f[i + 1] = g2.y; }
                     }
                     if (grow && p.aux_mode == 1) {
                         // residual epilogue: y = alpha[n] v + beta[n] res + delta[n] in fp32, one rounding

@@ -157,11 +157,27 @@ dw_strip_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
             float2 acc[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) acc[k] = bz;
+            // the shared-memory loads run kAhead input positions ahead of their use (they are volatile asm, i.e. kept in program order
+            // against the stores and barriers: issued right before their first use each one would expose its ~30-cycle latency)
+#ifndef CNA_STRIP_AHEAD_SMALLK
+#define CNA_STRIP_AHEAD_SMALLK 0
+#endif
+            constexpr int kAhead = (KX * K >= 9) ? 3 : CNA_STRIP_AHEAD_SMALLK;     // short strips (K <= 7): measured per K, see profiles/r02_strip_tma.txt
+            uint32_t q[kAhead + 1][KX];
+#pragma unroll
+            for (int i = 0; i < (kAhead > 0 ? kAhead : 1) && i < NIN; ++i)
+#pragma unroll
+                for (int rx = 0; rx < KX; ++rx) q[i][rx] = s_lds(src + (uint32_t)rx * in_line + (uint32_t)i * in_long);
 #pragma unroll
             for (int i = 0; i < NIN; ++i) {
+                if (i + kAhead < NIN && (kAhead > 0 || i > 0)) {
+#pragma unroll
+                    for (int rx = 0; rx < KX; ++rx)
+                        q[(i + kAhead) % (kAhead + 1)][rx] = s_lds(src + (uint32_t)rx * in_line + (uint32_t)(i + kAhead) * in_long);
+                }
 #pragma unroll
                 for (int rx = 0; rx < KX; ++rx) {                 // the KX box rows this line's window covers
-                    const float2 xv = s_unpack(s_lds(src + (uint32_t)rx * in_line + (uint32_t)i * in_long));
+                    const float2 xv = s_unpack(q[i % (kAhead + 1)][rx]);
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
                         const int o = i - k;                      // output fed by tap (rx, k) of input i
@@ -171,8 +187,7 @@ dw_strip_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                 if (i >= K - 1) {                                 // output i-K+1 has all its taps
                     const int o = i - (K - 1);
                     if constexpr (GELU) {
-                        acc[o % K].x = gelu_erf_fast(acc[o % K].x);
-                        acc[o % K].y = gelu_erf_fast(acc[o % K].y);
+                        acc[o % K] = gelu_erf_fast2(acc[o % K].x, acc[o % K].y);
                     }
                     __nv_bfloat162 r = __floats2bfloat162_rn(acc[o % K].x, acc[o % K].y);
                     s_sts(ob + out_thr + (uint32_t)o * out_long, *reinterpret_cast<uint32_t*>(&r));

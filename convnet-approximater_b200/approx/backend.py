@@ -42,6 +42,7 @@ _SIGS = {
     "cna_lowrank2_pack": "ppppiiiiiip",
     "cna_lowrank2_fused_forward": "pppppiiiiiiiiip",
     "cna_lowrank2_fused_supported": "iiiiii",
+    "cna_lowrank2_fused_plan": "iiiiip",
     "cna_lowrank2_fused_forward_t": "ppppppiiiiiiiip",
     "cna_tapconv3_tc_forward": "pppiiiiiip",
     "cna_wgrad3_tc": "pppiiiiiiiiip",
@@ -325,6 +326,15 @@ def conv1x1_tc_slab(a2d, k0, kc, w_nc, n0, nc, bias, y2d, act="none", aux2d=None
                                                     _p(alpha), _p(beta), _p(delta), off(y2d, n0), Ny, P, kc, nc, code, 1 if aux2d is not None else 0,
                                                     _stream(a2d)))
     return y2d
+
+
+def lowrank2_fused_plan(C: int, K: int, N: int, pool: bool = False, smem_limit: int = 232448) -> dict:
+    """Host-only: the fused scheme-2 kernel's shared-memory plan for a (C -> K -> N) layer (no device needed)."""
+    kp = 16 if K <= 16 else (32 if K <= 32 else 64)
+    out = (ctypes.c_int * 8)()
+    _check(lib().cna_lowrank2_fused_plan(round_up(C, 16), kp, int(N), int(bool(pool)), int(smem_limit), ctypes.addressof(out)))
+    keys = ("smem_bytes", "wv_resident", "wh_resident", "x_stages", "wh_slots", "store_buffers", "channel_chunk", "n_tile")
+    return dict(zip(keys, list(out)))
 
 
 def lowrank1_fused_supported(B, H, W, C, N, M, d, separable) -> bool:

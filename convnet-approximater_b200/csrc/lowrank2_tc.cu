@@ -884,6 +884,18 @@ int cna_lowrank2_fused_supported(int H, int W, int c_pad, int k_pad, int N, int 
     return plan_smem(p, CK, k_pad, NT2, 227 * 1024) != 0 ? 1 : 0;
 }
 
+int cna_lowrank2_fused_plan(int c_pad, int k_pad, int N, int pool, int smem_limit, int* out) {
+    CNA_CHECK(out != nullptr, "null pointer");
+    CNA_CHECK(shape_ok(8, 16, c_pad, k_pad, N, 3), "configuration not supported by the fused kernel");
+    LR2Params p{};
+    const int CK = pick_ck(c_pad), NT2 = pick_nt2(N);
+    p.N = N; p.nch = c_pad / CK; p.nn2 = N / NT2; p.pool = pool ? 1 : 0;
+    const size_t smem = plan_smem(p, CK, k_pad, NT2, (size_t)smem_limit);
+    CNA_CHECK(smem != 0, "shared-memory plan does not fit");
+    out[0] = (int)smem; out[1] = p.res_v; out[2] = p.res_h; out[3] = p.stages; out[4] = p.hslots; out[5] = p.nystg; out[6] = CK; out[7] = NT2;
+    return 0;
+}
+
 int cna_lowrank2_pack(const float* v_w, const float* h_w, void* wv_packed, void* wh_packed, int C, int K, int N, int d,
                       int c_pad, int k_pad, void* stream) {
     CNA_CHECK(v_w && h_w && wv_packed && wh_packed, "null pointer");

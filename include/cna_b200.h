@@ -175,6 +175,11 @@ int cna_lowrank2_fused_forward_traced(const void* x, const void* wv_packed, cons
                                       void* stream, long long* trace, int trace_tiles);
 /* 1 if the fused kernel supports this configuration, else 0 (caller falls back to two cna_conv_taps_forward). */
 int cna_lowrank2_fused_supported(int H, int W, int c_pad, int k_pad, int N, int d);
+/* The fused kernel's shared-memory plan for a layer, computed on the host without touching a device (for tests and tooling):
+ * out[0..7] = {dynamic smem bytes, Wv resident (0/1), Wh resident (0/1), x-ring stages, Wh-ring slots, TMA-store buffers per epilogue
+ * group, channel chunk CK, GEMM2 N-tile}.  smem_limit = the device's opt-in limit (232448 on B200).  Returns non-zero if the
+ * configuration is not supported or does not fit. */
+int cna_lowrank2_fused_plan(int c_pad, int k_pad, int N, int pool, int smem_limit, int* out);
 
 /* ---- MSCA fused depthwise chain ------------------------------------------------------------------ */
 /* s = [conv0(x)] + sum_b cascade_b(conv0(x))   (conv0: depthwise 5x5 + bias; cascade: depthwise 1xk + b1 then kx1 + b2,

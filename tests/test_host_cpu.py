@@ -166,6 +166,35 @@ def test_lowrank1_fused_plan_cpu():
     assert not B.lowrank1_fused_supported(4, 13, 13, 64, 272, 8, 3, False)    # 256 < N, N % 32 != 0
 
 
+def test_lowrank2_fused_plan_cpu():
+    """The fused scheme-2 kernel's shared-memory plan is pure host code: every VGG-16 layer at every rank bucket fits the 227 KB opt-in
+    limit with rings deep enough to pipeline, everything stays resident where it can, and partial residency (one of Wv / Wh resident,
+    the other streamed) appears exactly where it was measured to pay (<= 2 channel chunks or >= 4 N-tiles)."""
+    from approx import backend as B
+    vgg = [(3, 64), (64, 64), (64, 128), (128, 128), (128, 256), (256, 256), (256, 256), (256, 512), (512, 512), (512, 512),
+           (512, 512), (512, 512), (512, 512)]
+    pooled = {1, 3, 6, 9, 12}
+    for K in (4, 16, 32, 64):
+        for i, (C, N) in enumerate(vgg):
+            pl = B.lowrank2_fused_plan(C, K, N, pool=i in pooled)
+            assert pl["smem_bytes"] <= 232448, (K, i, pl)
+            assert pl["x_stages"] >= 2 and 1 <= pl["store_buffers"] <= 3, (K, i, pl)
+            assert pl["wh_resident"] or pl["wh_slots"] >= 3, (K, i, pl)
+            assert pl["channel_chunk"] == (16 if C == 3 else 64) and pl["n_tile"] == (64 if N == 64 else 128)
+            if pl["wv_resident"] and pl["wh_resident"]:
+                assert pl["x_stages"] >= 3, (K, i, pl)
+    full = lambda C, N, pool=False: B.lowrank2_fused_plan(C, 64, N, pool)
+    assert all(full(C, N)["wv_resident"] and full(C, N)["wh_resident"] for (C, N) in vgg[:4])       # 64- / 128-channel layers
+    p5, p6, p8, p9 = full(128, 256), full(256, 256), full(256, 512), full(512, 512)
+    assert (p5["wv_resident"], p5["wh_resident"]) == (0, 1) and (p8["wv_resident"], p8["wh_resident"]) == (1, 0)
+    assert (p6["wv_resident"], p6["wh_resident"]) == (0, 0) and (p9["wv_resident"], p9["wh_resident"]) == (0, 0)
+    assert full(3, 64)["store_buffers"] == 3                                                        # layer 1: smem to spare
+    with pytest.raises(RuntimeError):
+        B.lowrank2_fused_plan(64, 64, 72)                                                           # N % 64 != 0
+    with pytest.raises(RuntimeError):
+        B.lowrank2_fused_plan(64, 64, 64, smem_limit=48 * 1024)                                     # no opt-in shared memory
+
+
 def test_hook_registry_holds_the_reference_names_and_signatures():
     """approx.hooks: the names the shipped configs use, with the reference's constructor arguments (src/approx/hooks/*.py)."""
     import inspect

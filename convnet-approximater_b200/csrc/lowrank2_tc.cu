@@ -81,6 +81,8 @@ struct LR2Params {
     uint32_t off_y;               // y staging: kYBuf x (pool ? 1 : nystg) per epilogue group
     uint32_t off_p;               // pooled staging: 4 KB x nystg per epilogue group, only when pool
     int nystg;                    // TMA-store source buffers per epilogue group = stores a group keeps in flight (1..4)
+    int bias_mma;                 // 1: the bias enters through one extra K = 16 UMMA per N-tile (a ones column in TMEM against a [N][16] bias
+    uint32_t off_bm;              //    tile in smem at off_bm) instead of 64 FADD + 16 LDS per thread and item in the Y-epilogue
     uint32_t off_bias, off_bar;
     // optional: the T-epilogue also writes bf16 T = v_conv(x) to global memory (element strides: image, tile-row axis, tile-col
     // axis); t_only = 1 skips GEMM2 and the y path altogether (a plain 3-tap C -> KP convolution along the tile-row axis)
@@ -190,8 +192,13 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     constexpr int HROW = KP * 2;            // bytes per Wh smem row
     constexpr int ACOLS = KP / 2;           // TMEM columns of one bf16 copy of T
     constexpr int NABUF = NT2 == 64 ? 2 : 1;   // buffers of bf16 T copies (TMEM is full at NT2 = 128)
+    // The bias UMMA (p.bias_mma: the bias enters as one extra K = 16 MMA, the Y-epilogue adds nothing) is THE bias path of the
+    // 64-output-channel instances and absent from the 128-wide ones: measured per VGG layer on one box
+    // (profiles/r02_fused_conv_experiments.txt) it pays on layers 1-2 (-8 %, -3 %; K = 16: layer 1 -17 %), is neutral on layer 4 and
+    // costs 3.5 % on layer 3, and carrying both epilogue bodies in one instance costs ~2 % (spills in the 96-register CTA).
+    constexpr bool kBM = NT2 == 64;
     constexpr uint32_t kTmemT = 0, kTmemA = 128, kTmemY = kTmemA + NABUF * 96;   // NT2=64: 0/128/320, NT2=128: 0/128/224
-    static_assert(kTmemY + 2 * NT2 <= 512, "TMEM budget");
+    static_assert(kTmemY + 2 * NT2 + 8 <= 512, "TMEM budget (incl. the 8 columns of the bias UMMA's ones operand)");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -217,6 +224,21 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     }
     if (warp == 1) tmem_alloc<kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
     for (int i = threadIdx.x; i < p.N; i += kThreads) sbias[i] = bias ? bias[i] : 0.f;
+    if (kBM && p.bias_mma) {
+        // B operand of the bias UMMA: per N-tile a K-major [NT2 rows][16 k] bf16 tile in the 32-byte-swizzled layout TMA would write
+        // (16-byte chunk ^= bit 2 of the row): k = 0 holds bf16(b), k = 1 bf16(b - bf16(b)), the other 14 k are zero.
+        uint32_t* bm = reinterpret_cast<uint32_t*>(base_ptr + p.off_bm);
+        for (int i = threadIdx.x; i < p.N * 8; i += kThreads) bm[i] = 0u;
+        __syncthreads();
+        for (int n = threadIdx.x; n < p.N; n += kThreads) {
+            const float b = bias ? bias[n] : 0.f;
+            const __nv_bfloat16 hi = __float2bfloat16_rn(b), lo = __float2bfloat16_rn(b - __bfloat162float(hi));
+            const int r = n % NT2;
+            bm[(n / NT2) * (NT2 * 8) + r * 8 + (((r >> 2) & 1) ? 4 : 0)] =
+                (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+        }
+        fence_proxy_async_smem();
+    }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -224,6 +246,17 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     const uint32_t tmem_T = tmem + kTmemT;   // + buf*64
     const uint32_t tmem_A = tmem + kTmemA;   // + abuf*96 + dx*ACOLS
     const uint32_t tmem_Y = tmem + kTmemY;   // + yb*NT2
+    const uint32_t tmem_ones = tmem + kTmemY + 2 * NT2;      // A operand of the bias UMMA: 8 columns, k = 0, 1 are 1.0, the rest 0
+    if (kBM && p.bias_mma) {
+        if (warp >= 2 && warp < 6) {
+            const uint32_t ones[8] = {0x3F803F80u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            tmem_st8(tmem_ones + ((uint32_t)((warp & 3) * 32) << 16), ones);
+            tmem_st_wait();
+        }
+        tc_fence_before_sync();
+        __syncthreads();
+        tc_fence_after_sync();
+    }
 
     // diagnostic: row `trace_tiles` of the trace holds {clock64, globaltimer} at CTA 0's start and end (effective SM clock)
     auto stamp_wall = [&](int slot) {
@@ -349,6 +382,7 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         if (my_tiles > 0) {
             constexpr uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT2 >> 3) << 17) | (8u << 24);
             constexpr uint64_t hdesc = desc_hi(16, 8 * HROW, swz_type(HROW));
+            const uint64_t bmdesc = desc_hi(16, 8 * 32, swz_type(32)) + ((base + p.off_bm) >> 4);      // bias tile: 32-byte rows, 32B swizzle
             int hs = 0; uint32_t hph = 0;    // Wh ring
             if (p.res_h) { mbar_wait(bar(BAR_WFULL), 0); tc_fence_after_sync(); }
             for (int j = j0; j < my_tiles; j += jstep) {
@@ -382,6 +416,7 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                                 for (int kk = 0; kk < KP / 16; ++kk)
                                     umma_bf16_ts(d, tmem_A + (NABUF == 2 ? ab * 96 : 0) + dx * ACOLS + kk * 8, b0 + dx * slot16 + ((kk * 32) >> 4),
                                                  idesc2, (uint32_t)((dx | kk) != 0));
+                            if (kBM && p.bias_mma) umma_bf16_ts(d, tmem_ones, bmdesc + (uint64_t)((n2 * NT2 * 32) >> 4), idesc2, 1u);
                             umma_commit(bar(BAR_YACC_FULL + yb));
                             if (n2 == p.nn2 - 1) umma_commit(bar(BAR_TA_EMPTY + ab));
                         }
@@ -399,6 +434,7 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                                                  (uint32_t)((dx | kk) != 0));
                                 umma_commit(bar(BAR_HEMPTY + hs));
                                 if (dx == 2) {
+                                    if (kBM && p.bias_mma) umma_bf16_ts(d, tmem_ones, bmdesc + (uint64_t)((n2 * NT2 * 32) >> 4), idesc2, 1u);
                                     umma_commit(bar(BAR_YACC_FULL + yb));
                                     if (n2 == p.nn2 - 1) umma_commit(bar(BAR_TA_EMPTY + ab));
                                 }
@@ -534,7 +570,18 @@ lowrank2_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             if (++bi == nys) bi = 0;
             named_bar_sync(bar_a, 128);
             if (et == 0 && n2 == 0) stamp(j, 14);
-            if (valid && !(p.debug & 2)) {
+            if constexpr (kBM) { if (valid && !(p.debug & 2)) {
+                // the bias is already in the accumulator: round, ReLU, stage
+#pragma unroll
+                for (int ch = 0; ch < kNT / 8; ++ch) {
+                    uint32_t o0 = pack_bf16(__uint_as_float(v[ch * 8 + 0]), __uint_as_float(v[ch * 8 + 1]));
+                    uint32_t o1 = pack_bf16(__uint_as_float(v[ch * 8 + 2]), __uint_as_float(v[ch * 8 + 3]));
+                    uint32_t o2 = pack_bf16(__uint_as_float(v[ch * 8 + 4]), __uint_as_float(v[ch * 8 + 5]));
+                    uint32_t o3 = pack_bf16(__uint_as_float(v[ch * 8 + 6]), __uint_as_float(v[ch * 8 + 7]));
+                    if (p.relu) { o0 = relu_bf16x2(o0); o1 = relu_bf16x2(o1); o2 = relu_bf16x2(o2); o3 = relu_bf16x2(o3); }
+                    st_shared_v4_relaxed(sb + row_off + (((uint32_t)ch ^ sw) << 4), o0, o1, o2, o3);
+                }
+            } } else if (valid && !(p.debug & 2)) {
                 // bias chunks are fetched two chunks ahead of their use: a shared-memory load issued right before its
                 // first use costs the whole load latency eight times per item (short-scoreboard stalls in the profile)
                 const uint32_t bz = smem_u32(sbias + chan0);
@@ -684,11 +731,12 @@ static size_t plan_smem_mode(LR2Params& p, int CK, int KP, int NT2, size_t limit
     const uint32_t pool_bytes = p.pool ? 2 * ystg * 4096 : 0;
     const uint32_t ybytes = up1k((p.pool ? 2 : 2 * ystg) * kYBuf);
     const uint32_t xrow = CK * 2, hrow = KP * 2;
-    p.nystg = ystg; p.res_v = rv; p.res_h = rh;
+    p.nystg = ystg; p.res_v = rv; p.res_h = rh;      // (p.bias_mma is an input)
     p.x_stage = up1k(kXRows * kTileCols * xrow);
     p.v_chunk = up1k(3 * KP * xrow);
     p.h_slot = up1k(NT2 * hrow);
-    const size_t fixed = (size_t)ybytes + pool_bytes + up1k(p.N * 4) + 1024 /*barriers*/ + 1024 /*align slack*/ +
+    const uint32_t bm_bytes = p.bias_mma ? up1k(p.N * 32) : 0;       // [N][16] bf16 bias tile of the bias UMMA
+    const size_t fixed = (size_t)ybytes + pool_bytes + up1k(p.N * 4) + bm_bytes + 1024 /*barriers*/ + 1024 /*align slack*/ +
                          (rv ? (size_t)p.nch * p.v_chunk : 0) + (rh ? (size_t)3 * p.nn2 * p.h_slot : 0);
     const size_t per_stage = (size_t)p.x_stage + (rv ? 0 : p.v_chunk);
     for (int stages = kMaxStages; stages >= min_stages; --stages) {
@@ -703,6 +751,7 @@ static size_t plan_smem_mode(LR2Params& p, int CK, int KP, int NT2, size_t limit
         p.off_y = o; o += ybytes;
         p.off_p = o; o += pool_bytes;
         p.off_bias = o; o += up1k(p.N * 4);
+        p.off_bm = o; o += bm_bytes;
         p.off_bar = o;
         return (size_t)o + 2048;
     }
@@ -733,7 +782,7 @@ static size_t plan_smem_ystg(LR2Params& p, int CK, int KP, int NT2, size_t limit
 // Store-buffer depth: the deepest (<= kAutoYStg) that costs the plan neither its resident weights nor an x stage nor Wh slots below
 // a tile's worth; CNA_LR2_YSTG forces a depth (diagnostic sweeps), falling back towards 1 if it does not fit at all.
 constexpr int kAutoYStg = 3;
-static size_t plan_smem(LR2Params& p, int CK, int KP, int NT2, size_t limit) {
+static size_t plan_smem_nobm(LR2Params& p, int CK, int KP, int NT2, size_t limit) {
     static const int forced = [] { const char* e = getenv("CNA_LR2_YSTG"); return e ? std::max(1, std::min(4, atoi(e))) : 0; }();
     if (forced) {
         for (int y = forced; y >= 1; --y) { size_t s = plan_smem_ystg(p, CK, KP, NT2, limit, y); if (s) return s; }
@@ -750,6 +799,13 @@ static size_t plan_smem(LR2Params& p, int CK, int KP, int NT2, size_t limit) {
     }
     p = base;
     return s1;
+}
+
+// The bias UMMA (p.bias_mma) needs a [N][16] bf16 tile in shared memory (2 KB per 64 output channels): always on for the
+// 64-output-channel instances (the kernel has no other bias path there), never for the 128-wide ones or the 3-tap-only mode.
+static size_t plan_smem(LR2Params& p, int CK, int KP, int NT2, size_t limit) {
+    p.bias_mma = (NT2 == 64 && !p.t_only) ? 1 : 0;
+    return plan_smem_nobm(p, CK, KP, NT2, limit);
 }
 
 static bool shape_ok(int H, int W, int c_pad, int k_pad, int N, int d) {
@@ -830,8 +886,8 @@ static int lr2_launch(const void* x, const void* wv_packed, const void* wh_packe
     size_t smem = plan_smem(p, CK, k_pad, NT2, (size_t)max_smem);
     CNA_CHECK(smem != 0, "shared-memory plan does not fit");
     if (getenv("CNA_LR2_VERBOSE") != nullptr)
-        fprintf(stderr, "lowrank2 plan: C=%d K=%d N=%d H=%d W=%d pool=%d | CK=%d NT2=%d Wv %s Wh %s x-stages=%d hslots=%d ystg=%d smem=%zu\n", c_pad, k_pad,
-                N, H, W, pool, CK, NT2, p.res_v ? "resident" : "streamed", p.res_h ? "resident" : "streamed", p.stages, p.hslots, p.nystg, smem);
+        fprintf(stderr, "lowrank2 plan: C=%d K=%d N=%d H=%d W=%d pool=%d | CK=%d NT2=%d Wv %s Wh %s x-stages=%d hslots=%d ystg=%d bias_mma=%d smem=%zu\n", c_pad, k_pad,
+                N, H, W, pool, CK, NT2, p.res_v ? "resident" : "streamed", p.res_h ? "resident" : "streamed", p.stages, p.hslots, p.nystg, p.bias_mma, smem);
 
     CUtensorMap tm_x, tm_wv, tm_wh, tm_y;
     {

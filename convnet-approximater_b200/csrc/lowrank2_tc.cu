@@ -23,6 +23,9 @@
 //     128x64x16 UMMA costs ~73 cycles with A in shared memory and ~41 with A in TMEM, benchmarks/ubench_tcgen05.cu)
 //     and N = 128 output channels per instruction when the layer has them.
 //   * y tile: TMEM -> registers (+bias, ReLU) -> swizzled smem staging [-> 2x2 max-pool] -> TMA store (clips at edges).
+//     In the 64-output-channel instances the bias is not added by the epilogue: GEMM2 ends with one extra K = 16 UMMA whose A operand
+//     is a ones column pair in 8 spare TMEM columns and whose B operand is a [N][16] bf16 tile with bf16(b), bf16(b - bf16(b)) in its
+//     first two k (the bias to 16 mantissa bits, accumulated in fp32) - the epilogue there is issue-bound, the tensor pipe is not.
 //
 // Warp roles (640 threads, persistent CTAs, 1 per SM):
 //   warp 0      x / Wv TMA producer          warp 15     Wh TMA producer (own ring, so neither ring blocks the other)

@@ -139,3 +139,76 @@ def test_checkpoints_interchange_with_the_reference(cfg, tmp_path):
     assert list(a) == list(b)
     for k in a:
         assert a[k].shape == b[k].shape and torch.equal(a[k], b[k]), k
+
+
+CONVERTER_SCRIPT = r"""
+import runpy, sys, types
+for name in ("timm", "timm.data", "timm.models", "timm.utils", "timm.loss", "timm.optim", "timm.scheduler", "ptflops", "cvxpy"):
+    sys.modules.setdefault(name, types.ModuleType(name))
+import torch
+import approx.layers
+mode, script, cfg_file, ckpt = sys.argv[1:5]
+assert approx.layers.__file__.startswith("/root/reference") == (mode == "reference"), approx.layers.__file__
+if script == "make":
+    from approx.models import build_model
+    from approx.core import build_app
+    from approx.filters import build_filter
+    from approx.utils.config import Config
+    cfg = Config(); cfg.load_from_file(cfg_file)
+    torch.manual_seed(0)
+    model = build_model(cfg.model)
+    app = build_app(cfg.app, deploy=False)
+    filters = [build_filter(f) for f in cfg.filters] if 'filters' in cfg else []
+    model.register_switchable(app.src_type, filters)
+    for idx in range(model.length_switchable):
+        model.set_switchable_module(idx, app.initialize, src=model.get_switchable_module(idx))
+    torch.save(dict(state_dict=model.state_dict()), ckpt)
+else:
+    sys.argv = [script, "--config", cfg_file, "--ckpt", ckpt]
+    runpy.run_path(script, run_name="__main__")        # the reference's converter, unmodified
+print("converter ok")
+"""
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present on this machine")
+@pytest.mark.parametrize("cfg", ["configs/msca-rep/msca-rep_d1_fix_mscan-t.py",
+                                 "configs/low-rank-exp/low-rank-exp-v1_l2345_svd_alexnet.py"])   # (do_decomp needs the GPU)
+def test_reference_checkpoint_converters_run_on_this_backend(cfg, tmp_path):
+    """The reference's `scripts/ckpt_converter/remove_substitution.py` and `add_substitution.py`, run
+    unmodified on top of this backend's layers / apps (`deploy=True` and `postprocess` included): Substitution checkpoint →
+    deployed checkpoint → Substitution checkpoint.  The key lists equal the ones the unmodified reference produces, and the
+    replacement layers' tensors survive the round trip bit for bit."""
+    import torch
+    pkg = os.path.join(ROOT, "convnet-approximater_b200")
+    cfg_file = os.path.join("/root/reference", cfg)
+    conv = "/root/reference/scripts/ckpt_converter/"
+
+    def run(mode, script, ckpt):
+        if mode == "reference":
+            env = dict(os.environ, PYTHONPATH=REF)
+            env.pop("CNA_REFERENCE_SRC", None)
+        else:
+            env = dict(os.environ, CNA_REFERENCE_SRC=REF, PYTHONPATH=pkg)
+        out = subprocess.run([sys.executable, "-c", CONVERTER_SCRIPT, mode, script, cfg_file, ckpt], env=env,
+                             capture_output=True, text=True, cwd=str(tmp_path), timeout=600)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+        assert "converter ok" in out.stdout
+
+    got = {}
+    for mode in ("reference", "overlay"):
+        ckpt = str(tmp_path / f"{mode}.pth")
+        run(mode, "make", ckpt)
+        run(mode, conv + "remove_substitution.py", ckpt)
+        run(mode, conv + "add_substitution.py", str(tmp_path / f"{mode}_rm-sub.pth"))
+        got[mode] = [torch.load(str(tmp_path / (mode + sfx)), map_location="cpu")["state_dict"]
+                     for sfx in (".pth", "_rm-sub.pth", "_rm-sub_add-sub.pth")]
+    for ref_sd, our_sd in zip(got["reference"], got["overlay"]):
+        assert list(ref_sd) == list(our_sd)
+        assert all(ref_sd[k].shape == our_sd[k].shape for k in ref_sd)
+    sub, deployed, back = got["overlay"]
+    assert not any(".new." in k or ".old." in k for k in deployed)
+    assert list(sub) == list(back)
+    new_keys = [k for k in sub if ".new." in k]
+    assert new_keys
+    for k in new_keys:
+        assert torch.equal(sub[k], deployed[k.replace(".new.", ".")]) and torch.equal(sub[k], back[k]), k

@@ -4,7 +4,7 @@
 
 The reference times `module(x)` on the host clock (10 warm-up, 100 repeats); here the same loop is timed with CUDA events, for
   dense   stock nn.Conv2d through torch/cuDNN (the layer being replaced), in the run's dtype
-  ours    LowRankExpConvV1 of this backend (fused tcgen05 kernel for bf16 and num_base <= 8, unfused kernels otherwise)
+  ours    LowRankExpConvV1 of this backend (fused tcgen05 kernel for bf16 and num_base <= 16, unfused kernels otherwise)
 One JSON object per (layer, num_base).
 
     python benchmarks/low_rank_exp_spr.py [--decomp] [--dtype bf16|f32] [--batch 128]

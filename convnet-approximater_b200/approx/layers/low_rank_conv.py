@@ -65,12 +65,12 @@ class LowRankExpConvV1(nn.Module):
 
     def _fused(self, x):
         """One tcgen05 kernel for d_conv(s_conv(x)) (csrc/lowrank1_tc.cu) when the layer fits it: bf16, stride 1, 'same'.  The kernel
-        has instances for 4 and 8 bases per input channel; any other num_base <= 8 is padded up with zero bases (the reference's own
+        has instances for 4, 8 and 16 bases per input channel; any other num_base <= 16 is padded up with zero bases (the reference's own
         sweep, scripts/low_rank_exp_spr.py:35-63, walks num_base = 2..11)."""
         d = self.kernel_size[0]
         M = self.num_base
         sep = isinstance(self.s_conv, SeparableConv)
-        m_pad = 4 if M <= 4 else (8 if M <= 8 else 0)
+        m_pad = 4 if M <= 4 else (8 if M <= 8 else (16 if M <= 16 else 0))
         if not (m_pad and x.dtype == torch.bfloat16 and x.is_contiguous() and self.kernel_size == (d, d) and self.stride == (1, 1)
                 and self.padding == (d // 2, d // 2) and (self.in_channels * m_pad) % 64 == 0
                 and B.lowrank1_fused_supported(*x.shape[:3], self.in_channels, self.out_channels, m_pad, d, sep)):

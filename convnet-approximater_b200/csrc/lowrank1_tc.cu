@@ -134,6 +134,8 @@ lowrank1_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                       const float* __restrict__ s_packed, const float* __restrict__ d_bias, __nv_bfloat16* __restrict__ y,
                       const L1Params p) {
     constexpr int CPC = 64 / M;                  // input channels per K-chunk
+    constexpr int CBOX = CPC < 8 ? 8 : CPC;      // channels per pixel of the staged x box: TMA's inner extent is >= 16 bytes, so the
+                                                 // 16-basis instance stages an aligned octet per chunk and uses one half of it
     constexpr int NCU = (M >= 8) ? 1 : 8 / M;    // input channels behind one 8-wide unit
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -178,8 +180,11 @@ lowrank1_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                     const uint32_t dst = base + p.off_xs + xs * p.xs_stage;
                     const bool skip_x = (p.debug & 8) != 0;
                     mbar_arrive_expect_tx(bar(L1_XS_FULL + xs), (skip_x ? 0u : (two ? 2u : 1u) * p.seg_box_bytes) + p.wblk_bytes);
-                    if (!skip_x) tma_load_4d(dst, &tm_x, bar(L1_XS_FULL + xs), ch * CPC, -p.pad, h0 - p.pad, b0);
-                    if (two && !skip_x) tma_load_4d(dst + p.seg_bytes, &tm_x, bar(L1_XS_FULL + xs), ch * CPC, -p.pad, -p.pad - R1, b0 + 1);
+                    // first channel of the box: the chunk's own, or (16 bases: 4 channels per chunk, 8 per box) the enclosing 16-byte
+                    // aligned channel octet — the producers then read its lower or upper half
+                    const int c0 = CPC < 8 ? (ch * CPC) / 8 * 8 : ch * CPC;
+                    if (!skip_x) tma_load_4d(dst, &tm_x, bar(L1_XS_FULL + xs), c0, -p.pad, h0 - p.pad, b0);
+                    if (two && !skip_x) tma_load_4d(dst + p.seg_bytes, &tm_x, bar(L1_XS_FULL + xs), c0, -p.pad, -p.pad - R1, b0 + 1);
                     l1_bulk_load(dst + 2 * p.seg_bytes, s_packed + (size_t)ch * (p.wblk_bytes / 4), p.wblk_bytes, bar(L1_XS_FULL + xs));
                 }
                 __syncwarp();
@@ -274,7 +279,7 @@ lowrank1_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             for (int k = 0; k < 4; ++k) {
                 rk[k] = rr; wk[k] = 4 * cj + k;
                 const int m = rr * p.WS + wk[k];
-                xoff[k] = rr < p.R ? (uint32_t)((rr * p.WP + 4 * cj) * CPC + u) * 2u : (uint32_t)u * 2u;      // the run's first column
+                xoff[k] = rr < p.R ? (uint32_t)((rr * p.WP + 4 * cj) * CBOX + u) * 2u : (uint32_t)u * 2u;      // the run's first column
                 aoff[k] = (uint32_t)m * 128u + (uint32_t)((u ^ (m & 7)) * 16);
             }
         } else {
@@ -284,11 +289,11 @@ lowrank1_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 rk[k] = m / p.W;
                 wk[k] = m - rk[k] * p.W;
                 // slots past the tile (rk >= R) compute on slot 0's data and are never stored
-                xoff[k] = rk[k] < p.R ? (uint32_t)((rk[k] * p.WP + wk[k]) * CPC + (u * 8) / M) * 2u : (uint32_t)((u * 8) / M) * 2u;
+                xoff[k] = rk[k] < p.R ? (uint32_t)((rk[k] * p.WP + wk[k]) * CBOX + (u * 8) / M) * 2u : (uint32_t)((u * 8) / M) * 2u;
                 aoff[k] = (uint32_t)m * 128u + (uint32_t)((u ^ (m & 7)) * 16);      // 128B swizzle: 16-byte unit u of row m lands at u ^ (m % 8)
             }
         }
-        const uint32_t row_pitch = (uint32_t)p.WP * CPC * 2u;
+        const uint32_t row_pitch = (uint32_t)p.WP * CBOX * 2u;
         const uint32_t a_addr = base + p.off_a + grp * p.a_buf;
         uint32_t q = 0;                                   // chunk counter over this CTA's tiles
         L1Prof pf(p.prof, pt == 0);
@@ -316,6 +321,11 @@ lowrank1_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 uint32_t xr[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) xr[k] = stage + xo[k];
+                if constexpr (CPC < 8) {                          // this chunk's channels within the staged octet
+                    const uint32_t half = (uint32_t)((ch * CPC) % 8) * 2u;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) xr[k] += half;
+                }
                 if constexpr (HRUN && !SEP) {
                     float2 acc[4][4];
                     float2 bs[4];
@@ -331,7 +341,7 @@ lowrank1_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                             float2 X[D + 3];                                  // the row's inputs, each feeding up to D taps x 4 outputs
                             l1_static_for<0, D + 3>([&](auto cc) {
                                 constexpr int c = decltype(cc)::value;
-                                const float v = l1_lds_bf16<c * (CPC * 2)>(xrow);
+                                const float v = l1_lds_bf16<c * (CBOX * 2)>(xrow);
                                 X[c] = make_float2(v, v);
                             });
                             l1_static_for<0, D>([&](auto jc) {
@@ -368,7 +378,7 @@ lowrank1_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                             for (int e = 0; e < 4; ++e) tc[e] = make_float2(0.f, 0.f);
                             l1_static_for<0, D>([&](auto ic) {
                                 constexpr int i = decltype(ic)::value;
-                                const float v = l1_lds_bf16<c * (CPC * 2)>(xrow[i]);
+                                const float v = l1_lds_bf16<c * (CBOX * 2)>(xrow[i]);
                                 float2 w[4];
                                 l1_lds_f8<i * 256>(wb, w);                        // v taps: rows 0 .. D-1
 #pragma unroll
@@ -412,7 +422,7 @@ lowrank1_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                                     float xv[NCU];
                                     l1_static_for<0, NCU>([&](auto cc) {
                                         constexpr int c = decltype(cc)::value;
-                                        xv[c] = l1_lds_bf16<j * (CPC * 2) + 2 * c>(xr[k]);
+                                        xv[c] = l1_lds_bf16<j * (CBOX * 2) + 2 * c>(xr[k]);
                                     });
 #pragma unroll
                                     for (int e = 0; e < 4; ++e) {
@@ -456,7 +466,7 @@ lowrank1_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                                         float xv[NCU];
                                         l1_static_for<0, NCU>([&](auto cc) {
                                             constexpr int c = decltype(cc)::value;
-                                            xv[c] = l1_lds_bf16<j * (CPC * 2) + 2 * c>(xc[kk]);
+                                            xv[c] = l1_lds_bf16<j * (CBOX * 2) + 2 * c>(xc[kk]);
                                         });
 #pragma unroll
                                         for (int e = 0; e < 4; ++e) {
@@ -580,9 +590,10 @@ static uint32_t l1_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 // Fills the tile / shared-memory plan; returns the dynamic smem bytes (incl. alignment slack) or 0 when the layer is not covered.
 static size_t l1_plan(L1Params& p, int B, int H, int W, int C, int N, int M, int d, int separable, size_t limit) {
-    if (!(d == 3 || d == 5) || !(M == 4 || M == 8)) return 0;
+    if (!(d == 3 || d == 5) || !(M == 4 || M == 8 || M == 16)) return 0;
     if (B <= 0 || H <= 0 || W <= 0 || W > 128) return 0;
     const int cpc = 64 / M;
+    const int cbox = std::max(cpc, 8);          // channels per pixel of the x box (kernel: CBOX)
     if (C <= 0 || C % cpc != 0 || C % 8 != 0) return 0;
     if (N < 16 || N % 16 != 0 || N > 512 || (N > 256 && N % 32 != 0)) return 0;
     if ((long long)B * H > (1LL << 30)) return 0;
@@ -609,7 +620,7 @@ static size_t l1_plan(L1Params& p, int B, int H, int W, int C, int N, int M, int
     p.nbuf = N <= 256 ? 2 : 1;
     p.WP = W + 2 * p.pad; p.RP = p.R + 2 * p.pad;
     if (p.WP > 256 || p.RP > 256) return 0;
-    p.seg_box_bytes = (uint32_t)(cpc * 2 * p.WP * p.RP);
+    p.seg_box_bytes = (uint32_t)(cbox * 2 * p.WP * p.RP);
     p.seg_bytes = l1_up(p.seg_box_bytes, 128);
     p.wblk_bytes = (uint32_t)((separable ? 2 * d : d * d + 1) * 64 * 4);
     p.xs_stage = l1_up(2 * p.seg_bytes + p.wblk_bytes, 128);
@@ -663,7 +674,7 @@ int cna_lowrank1_fused_forward(const void* x, const float* s_packed, const void*
     L1Params p{};
     const size_t smem = l1_plan(p, B, H, W, C, N, M, d, separable, 227 * 1024);
     CNA_CHECK(smem != 0, "configuration not covered by the fused scheme-1 kernel (bf16, stride 1, 'same' padding, d in {3,5}, "
-                         "M in {4,8}, C*M % 64 == 0, C % 8 == 0, N % 16 == 0, N <= 512, W <= 128)");
+                         "M in {4,8,16}, C*M % 64 == 0, C % 8 == 0, N % 16 == 0, N <= 512, W <= 128)");
     DevInfo di;
     if (dev_info(&di)) return 1;
     const int num_sms = di.num_sms;
@@ -671,7 +682,7 @@ int cna_lowrank1_fused_forward(const void* x, const float* s_packed, const void*
     {
         cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
         cuuint64_t str[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-        cuuint32_t box[4] = {(cuuint32_t)(64 / M), (cuuint32_t)p.WP, (cuuint32_t)p.RP, 1};
+        cuuint32_t box[4] = {(cuuint32_t)std::max(64 / M, 8), (cuuint32_t)p.WP, (cuuint32_t)p.RP, 1};   // CBOX channels
         if (l1_encode(&tm_x, x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
     }
     {
@@ -701,6 +712,8 @@ int cna_lowrank1_fused_forward(const void* x, const float* s_packed, const void*
     CNA_L1_CASE(5, 8)
     CNA_L1_CASE(3, 4)
     CNA_L1_CASE(5, 4)
+    CNA_L1_CASE(3, 16)
+    CNA_L1_CASE(5, 16)
 #undef CNA_L1_CASE
     if (p.hrun && M == 8 && d == 3)
         rc = separable ? l1_launch<3, 8, true, true>(tm_x, tm_w, s_packed, d_bias, y, p, smem, grid, st)

@@ -126,10 +126,10 @@ def test_random_shapes_agree_with_unfused_path():
 
 
 @pytest.mark.parametrize("sep", [False, True])
-@pytest.mark.parametrize("M", [2, 3, 5, 6, 7])
+@pytest.mark.parametrize("M", [2, 3, 5, 6, 7, 9, 10, 11, 16])
 def test_num_base_outside_4_and_8_runs_fused_by_padding(M, sep):
-    """The reference's own sweep (scripts/low_rank_exp_spr.py:35-63) walks num_base = 2..11: every M <= 8 stays on the fused kernel
-    (padded with zero bases to the 4- or 8-basis instance) and still matches the bf16 oracle."""
+    """The reference's own sweep (scripts/low_rank_exp_spr.py:35-63) walks num_base = 2..11: every M <= 16 stays on the fused kernel
+    (padded with zero bases to the 4-, 8- or 16-basis instance) and still matches the bf16 oracle."""
     from approx import backend as B
     C, N, d, H = 64, 96, 3, 13
     m = build(C, N, d, M, sep, 11 + M)
@@ -144,3 +144,29 @@ def test_num_base_outside_4_and_8_runs_fused_by_padding(M, sep):
         y = mg.forward_nhwc(xn)
         assert B.launch_count() - before == 1, "expected exactly the fused kernel"
     assert O.compare4d(ref, y.permute(0, 3, 1, 2).float().cpu()) < 1e-3
+
+
+@pytest.mark.parametrize("Bn,C,N,d,M,H,W,sep", [
+    (3, 8, 32, 3, 16, 13, 13, False),        # one channel octet = two chunks, tiles straddle images
+    (2, 72, 64, 3, 12, 27, 27, True),        # 18 chunks, 12 bases padded to 16, decomposed form
+    (2, 24, 192, 5, 9, 27, 27, False),       # 5x5 taps (AlexNet conv2 geometry), 9 -> 16
+    (2, 40, 48, 5, 16, 9, 20, True),         # 5x5 separable, W != H, ragged last tile
+    (5, 192, 384, 3, 11, 13, 13, False),     # AlexNet conv3 at num_base 11: two N-tiles share every A slab
+])
+def test_sixteen_basis_instance_vs_oracle(Bn, C, N, d, M, H, W, sep):
+    """num_base 9..16 run on the 16-basis instance (4 input channels per 64-wide chunk; the staged x box is the enclosing channel
+    octet, of which a chunk reads one half): one launch, bf16 oracle within 1e-3 (compare4d, reference tests/test_low_rank_exp.py:5-14)."""
+    from approx import backend as B
+    m = build(C, N, d, M, sep, 100 + M + C)
+    x = torch.randn(Bn, C, H, W, generator=torch.Generator().manual_seed(5)).bfloat16()
+    with torch.no_grad():
+        ref = oracle(m, x, sep).float()
+    mg = m.cuda().eval()
+    xn = B.to_nhwc(x.cuda())
+    with torch.no_grad():
+        mg.forward_nhwc(xn)
+        before = B.launch_count()
+        y = mg.forward_nhwc(xn)
+        assert B.launch_count() - before == 1, "expected exactly the fused kernel"
+    err = O.compare4d(ref, y.permute(0, 3, 1, 2).float().cpu())
+    assert err < 1e-3, (Bn, C, N, d, M, H, W, sep, err)

@@ -94,3 +94,20 @@ def check_input(x: torch.Tensor):
         raise ValueError(f"expected a (B,C,H,W) tensor, got shape {tuple(x.shape)}")
     B.require_cuda(x)
     B.dtype_code(x.dtype)
+
+
+def empty_batch_safe(forward):
+    """A batch of zero images.  The reference's layers are stacks of `nn.Conv2d`, which take one and return a batch of zero outputs
+    (e.g. the tail of a sharded loader); the kernels here have no zero-sized launch, so the output's shape and dtype are taken from
+    one zero image pushed through the same kernels."""
+    import functools
+
+    @functools.wraps(forward)
+    def wrapper(self, x, *args, **kwargs):
+        if isinstance(x, torch.Tensor) and x.dim() == 4 and x.shape[0] == 0 and min(x.shape[1:]) > 0:
+            check_input(x)
+            with torch.no_grad():
+                y = forward(self, x.new_zeros((1,) + tuple(x.shape[1:])), *args, **kwargs)
+            return y[:0]
+        return forward(self, x, *args, **kwargs)
+    return wrapper

@@ -25,6 +25,7 @@ class CascadeConv(nn.Module):
     def forward_nhwc(self, x, res=None, add=None):
         return _ops.dw(self.conv2, _ops.dw(self.conv1, x), res=res, add=add)
 
+    @_ops.empty_batch_safe
     def forward(self, x):
         _ops.check_input(x)
         return B.from_nhwc(self.forward_nhwc(B.to_nhwc(x)))
@@ -68,6 +69,7 @@ class ParallelConv(nn.Module):
             acc = B.add(acc, x)
         return acc
 
+    @_ops.empty_batch_safe
     def forward(self, x):
         _ops.check_input(x)
         return B.from_nhwc(self.forward_nhwc(B.to_nhwc(x)))
@@ -91,6 +93,8 @@ class FixPaddingBias(nn.Module):
 
     def forward(self, x):
         _ops.check_input(x)
+        if x.numel() == 0:              # nothing to patch (the reference's slice assignments are no-ops on an empty batch)
+            return x
         v = x.permute(0, 2, 3, 1)
         if v.is_contiguous():           # channels_last: patch the caller's storage directly
             self.forward_nhwc_(v)

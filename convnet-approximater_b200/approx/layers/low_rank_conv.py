@@ -30,6 +30,7 @@ class SeparableConv(nn.Module):
     def forward_nhwc(self, x):
         return _ops.dw(self.h_conv, _ops.dw(self.v_conv, x))
 
+    @_ops.empty_batch_safe
     def forward(self, x):
         _ops.check_input(x)
         return B.from_nhwc(self.forward_nhwc(B.to_nhwc(x)))
@@ -89,6 +90,7 @@ class LowRankExpConvV1(nn.Module):
         t = self.s_conv.forward_nhwc(x) if isinstance(self.s_conv, SeparableConv) else _ops.dw(self.s_conv, x)
         return _ops.dense_taps(self.d_conv, t)
 
+    @_ops.empty_batch_safe
     def forward(self, x):
         _ops.check_input(x)
         # model.train() + autograd (the reference's L2Reconstruct fine-tuning of the AlexNet layers): op-by-op path with backward
@@ -222,6 +224,7 @@ class LowRankExpConvV2(nn.Module):
         return (self.dense and self.stride == (1, 1) and kh % 2 == 1 and kw % 2 == 1
                 and self.padding == (kh // 2, kw // 2))
 
+    @_ops.empty_batch_safe
     def forward(self, x):
         _ops.check_input(x)
         # Backward kernels cover the dense scheme-2 layer with stride 1 and 'same' padding.  Every other form runs

@@ -49,6 +49,7 @@ class MSCA(nn.Module):
             a = run_sd_convs(self.sd_convs, _ops.dw(self.conv0, x))
         return _ops.dense_taps(self.channel_mix, a, gate=x)
 
+    @_ops.empty_batch_safe
     def forward(self, x):
         _ops.check_input(x)
         # model.train() + autograd (the reference's L2Reconstruct fine-tuning, hooks/finetune.py:275,329): op-by-op path with

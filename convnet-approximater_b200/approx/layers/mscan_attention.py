@@ -70,6 +70,7 @@ class MSCANAttention(nn.Module):
         v = self.attn.spatial_gating_unit.forward_nhwc(u)
         return B.conv1x1_tc_ex(v, w2p, b2, residual=x, alpha=alpha, beta=beta, delta=delta)
 
+    @_ops.empty_batch_safe
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         _ops.check_input(x)
         return B.from_nhwc(self.forward_nhwc(B.to_nhwc(x)))

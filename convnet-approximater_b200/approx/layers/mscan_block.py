@@ -95,6 +95,7 @@ class MSCANFFN(nn.Module):
                 B.conv1x1_tc_slab(g2, k0, kc, w2p, 0, C, None, y2, aux2d=y2, alpha=ls)
         return y
 
+    @_ops.empty_batch_safe
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         _ops.check_input(x)
         return B.from_nhwc(self.forward_nhwc(B.to_nhwc(x)))
@@ -126,6 +127,7 @@ class MSCANBlock(nn.Module):
     def forward_nhwc(self, x: torch.Tensor) -> torch.Tensor:
         return self._ffn_half.forward_nhwc(self._attn_half.forward_nhwc(x))
 
+    @_ops.empty_batch_safe
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         _ops.check_input(x)
         return B.from_nhwc(self.forward_nhwc(B.to_nhwc(x)))

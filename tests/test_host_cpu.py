@@ -159,7 +159,9 @@ def test_lowrank1_fused_plan_cpu():
     assert B.lowrank1_fused_supported(1, 7, 128, 8, 16, 8, 3, False)          # W = 128: one row per tile
     assert not B.lowrank1_fused_supported(1, 7, 129, 8, 16, 8, 3, False)      # wider than a tile
     assert not B.lowrank1_fused_supported(4, 13, 13, 64, 192, 8, 7, False)    # 7x7 bases: no instance
-    assert not B.lowrank1_fused_supported(4, 13, 13, 64, 192, 16, 3, False)   # M = 16: 4 channels per chunk < 16-byte TMA rows
+    assert B.lowrank1_fused_supported(4, 13, 13, 64, 192, 16, 3, False)       # M = 16: 4 channels per chunk, staged as aligned octets
+    assert not B.lowrank1_fused_supported(4, 13, 13, 64, 192, 32, 3, False)   # M = 32: no instance
+    assert not B.lowrank1_fused_supported(4, 13, 13, 12, 192, 16, 3, False)   # C % 8 != 0
     assert not B.lowrank1_fused_supported(4, 13, 13, 12, 192, 8, 3, False)    # C % 8 != 0
     assert not B.lowrank1_fused_supported(4, 13, 13, 64, 200, 8, 3, False)    # N % 16 != 0
     assert not B.lowrank1_fused_supported(4, 13, 13, 64, 528, 8, 3, False)    # N > 512

@@ -465,3 +465,30 @@ assert e1 < 1e-2, e1
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env={**os.environ, **env},
                        capture_output=True, text=True, timeout=200)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_empty_batch_returns_empty_outputs_like_the_reference_layers():
+    """A batch of zero images: the reference's layers (stacks of nn.Conv2d) return a batch of zero outputs; so do these, with the
+    shape and dtype the stock convs give on the same empty input."""
+    from approx.layers import LowRankExpConvV1, LowRankExpConvV2, MSCA, CascadeConv, ParallelConv, FixPaddingBias
+    from torch import nn
+    torch.manual_seed(0)
+    cases = [
+        (LowRankExpConvV2(16, 8, (3, 3), (1, 1), (1, 1), out_channels=32), (0, 16, 12, 10),
+         nn.Sequential(nn.Conv2d(16, 8, (3, 1), 1, (1, 0), bias=False), nn.Conv2d(8, 32, (1, 3), 1, (0, 1)))),
+        (LowRankExpConvV2(16, 8, (3, 3), (2, 2), (1, 1)), (0, 16, 12, 10),
+         nn.Sequential(nn.Conv2d(16, 8, (3, 1), (2, 1), (1, 0), bias=False), nn.Conv2d(8, 8, (1, 3), (1, 2), (0, 1), groups=8))),
+        (LowRankExpConvV1(8, 16, 3, 1, 1, num_base=4), (0, 8, 9, 9), nn.Conv2d(8, 16, 3, 1, 1)),
+        (LowRankExpConvV1(8, 16, 5, 2, 2, num_base=3, decomp=True), (0, 8, 9, 9), nn.Conv2d(8, 16, 5, 2, 2)),
+        (MSCA(32, 5, (7, 11, 21)), (0, 32, 16, 16), nn.Identity()),
+        (CascadeConv(8, 7, 3, True, False), (0, 8, 6, 6), nn.Identity()),
+        (ParallelConv(8, (7, 11), (3, 5), 2, True, True), (0, 8, 6, 6), nn.Identity()),
+        (FixPaddingBias(8, 10), (0, 8, 6, 6), nn.Identity()),
+    ]
+    for dtype in (torch.float32, torch.bfloat16):
+        for layer, shape, stock in cases:
+            x = torch.zeros(shape, dtype=dtype)
+            want = stock.to(dtype)(x)
+            with torch.no_grad():
+                got = layer.to("cuda", dtype).eval()(x.cuda())
+            assert got.shape == want.shape and got.dtype == want.dtype and got.is_cuda, (type(layer).__name__, got.shape, want.shape)

@@ -590,7 +590,7 @@ static uint32_t l1_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 // Fills the tile / shared-memory plan; returns the dynamic smem bytes (incl. alignment slack) or 0 when the layer is not covered.
 static size_t l1_plan(L1Params& p, int B, int H, int W, int C, int N, int M, int d, int separable, size_t limit) {
-    if (!(d == 3 || d == 5) || !(M == 4 || M == 8 || M == 16)) return 0;
+    if (!(d == 3 || d == 5) || !(M == 2 || M == 4 || M == 8 || M == 16)) return 0;
     if (B <= 0 || H <= 0 || W <= 0 || W > 128) return 0;
     const int cpc = 64 / M;
     const int cbox = std::max(cpc, 8);          // channels per pixel of the x box (kernel: CBOX)
@@ -674,7 +674,7 @@ int cna_lowrank1_fused_forward(const void* x, const float* s_packed, const void*
     L1Params p{};
     const size_t smem = l1_plan(p, B, H, W, C, N, M, d, separable, 227 * 1024);
     CNA_CHECK(smem != 0, "configuration not covered by the fused scheme-1 kernel (bf16, stride 1, 'same' padding, d in {3,5}, "
-                         "M in {4,8,16}, C*M % 64 == 0, C % 8 == 0, N % 16 == 0, N <= 512, W <= 128)");
+                         "M in {2,4,8,16}, C*M % 64 == 0, C % 8 == 0, N % 16 == 0, N <= 512, W <= 128)");
     DevInfo di;
     if (dev_info(&di)) return 1;
     const int num_sms = di.num_sms;
@@ -714,6 +714,8 @@ int cna_lowrank1_fused_forward(const void* x, const float* s_packed, const void*
     CNA_L1_CASE(5, 4)
     CNA_L1_CASE(3, 16)
     CNA_L1_CASE(5, 16)
+    CNA_L1_CASE(3, 2)
+    CNA_L1_CASE(5, 2)
 #undef CNA_L1_CASE
     if (p.hrun && M == 8 && d == 3)
         rc = separable ? l1_launch<3, 8, true, true>(tm_x, tm_w, s_packed, d_bias, y, p, smem, grid, st)

@@ -108,7 +108,7 @@ int cna_conv1x1_tc_forward_strided(const void* a, long long lda, const void* w_p
  *               separable == 1: [d v-taps][64] then [d h-taps][64]                                (SeparableConv, bias-free)
  *   dw_packed bf16 [N][C*M] (cna_conv1x1_pack of d_conv.weight), d_bias fp32 (N,) or NULL
  *   y         (B,H,W,N) bf16
- * Covered: d in {3,5}, M in {4,8,16}, C*M % 64 == 0, C % 8 == 0, N % 16 == 0, N <= 512 (N % 32 == 0 above 256), W <= 128;
+ * Covered: d in {3,5}, M in {2,4,8,16}, C*M % 64 == 0, C % 8 == 0, N % 16 == 0, N <= 512 (N % 32 == 0 above 256), W <= 128;
  * everything else stays on cna_dwconv_forward + cna_conv1x1_tc_forward / cna_conv_taps_forward. */
 int cna_lowrank1_fused_supported(int B, int H, int W, int C, int N, int M, int d, int separable);
 int cna_lowrank1_fused_forward(const void* x, const float* s_packed, const void* dw_packed, const float* d_bias, void* y, int B, int H,

@@ -161,6 +161,8 @@ def test_lowrank1_fused_plan_cpu():
     assert not B.lowrank1_fused_supported(4, 13, 13, 64, 192, 8, 7, False)    # 7x7 bases: no instance
     assert B.lowrank1_fused_supported(4, 13, 13, 64, 192, 16, 3, False)       # M = 16: 4 channels per chunk, staged as aligned octets
     assert not B.lowrank1_fused_supported(4, 13, 13, 64, 192, 32, 3, False)   # M = 32: no instance
+    assert B.lowrank1_fused_supported(4, 13, 13, 64, 192, 2, 5, True)         # M = 2: 32 channels per chunk
+    assert not B.lowrank1_fused_supported(4, 13, 13, 48, 192, 2, 3, False)    # ... which must divide C
     assert not B.lowrank1_fused_supported(4, 13, 13, 12, 192, 16, 3, False)   # C % 8 != 0
     assert not B.lowrank1_fused_supported(4, 13, 13, 12, 192, 8, 3, False)    # C % 8 != 0
     assert not B.lowrank1_fused_supported(4, 13, 13, 64, 200, 8, 3, False)    # N % 16 != 0

@@ -129,7 +129,7 @@ def test_random_shapes_agree_with_unfused_path():
 @pytest.mark.parametrize("M", [2, 3, 5, 6, 7, 9, 10, 11, 16])
 def test_num_base_outside_4_and_8_runs_fused_by_padding(M, sep):
     """The reference's own sweep (scripts/low_rank_exp_spr.py:35-63) walks num_base = 2..11: every M <= 16 stays on the fused kernel
-    (padded with zero bases to the 4-, 8- or 16-basis instance) and still matches the bf16 oracle."""
+    (padded with zero bases to the 2-, 4-, 8- or 16-basis instance) and still matches the bf16 oracle."""
     from approx import backend as B
     C, N, d, H = 64, 96, 3, 13
     m = build(C, N, d, M, sep, 11 + M)
@@ -152,10 +152,14 @@ def test_num_base_outside_4_and_8_runs_fused_by_padding(M, sep):
     (2, 24, 192, 5, 9, 27, 27, False),       # 5x5 taps (AlexNet conv2 geometry), 9 -> 16
     (2, 40, 48, 5, 16, 9, 20, True),         # 5x5 separable, W != H, ragged last tile
     (5, 192, 384, 3, 11, 13, 13, False),     # AlexNet conv3 at num_base 11: two N-tiles share every A slab
+    (2, 64, 192, 5, 2, 27, 27, False),       # 2-basis instance: 32 input channels per chunk, AlexNet conv2 geometry
+    (3, 96, 64, 5, 2, 9, 20, True),          # 2 bases, 3 chunks, separable 5 + 5, W != H
+    (4, 256, 256, 3, 2, 7, 7, False),        # the sweep's conv5 point at num_base 2 (7 x 7 images: 49 of 128 tile rows)
 ])
-def test_sixteen_basis_instance_vs_oracle(Bn, C, N, d, M, H, W, sep):
+def test_two_and_sixteen_basis_instances_vs_oracle(Bn, C, N, d, M, H, W, sep):
     """num_base 9..16 run on the 16-basis instance (4 input channels per 64-wide chunk; the staged x box is the enclosing channel
-    octet, of which a chunk reads one half): one launch, bf16 oracle within 1e-3 (compare4d, reference tests/test_low_rank_exp.py:5-14)."""
+    octet, of which a chunk reads one half), num_base 2 on the 2-basis instance (32 input channels per chunk) when C % 32 == 0:
+    one launch, bf16 oracle within 1e-3 (compare4d, reference tests/test_low_rank_exp.py:5-14)."""
     from approx import backend as B
     m = build(C, N, d, M, sep, 100 + M + C)
     x = torch.randn(Bn, C, H, W, generator=torch.Generator().manual_seed(5)).bfloat16()
@@ -170,3 +174,47 @@ def test_sixteen_basis_instance_vs_oracle(Bn, C, N, d, M, H, W, sep):
         assert B.launch_count() - before == 1, "expected exactly the fused kernel"
     err = O.compare4d(ref, y.permute(0, 3, 1, 2).float().cpu())
     assert err < 1e-3, (Bn, C, N, d, M, H, W, sep, err)
+
+
+def test_plan_record_follows_weight_updates_decomp_and_invalidate():
+    """The fused path keeps the last call's decision and packed operands in one record (the small layers are host-bound at the
+    reference's profiling batches).  It must notice `.weight.data = ...` assignments (the reference's write-back,
+    core/low_rank_exp.py:181-184), `decomp()` replacing `s_conv` (layers/low_rank_conv.py:58-66), `_ops.invalidate` after an in-place
+    edit through `.data`, a different input shape, and the train()/no-grad switch — each time against the bf16 oracle."""
+    from approx import backend as B
+    from approx.layers import _ops
+    C, N, d, M, H = 64, 96, 3, 4, 13
+    m = build(C, N, d, M, False, 41)
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(4, C, H, H, generator=g).bfloat16()
+    mg = m.cuda().eval()
+    xg = x.cuda().contiguous(memory_format=torch.channels_last)
+
+    def check(xc, xd, sep):
+        twin = build(C, N, d, M, sep, 0)                   # CPU module holding mg's current parameters, for the oracle
+        twin.load_state_dict({k: v.cpu() for k, v in mg.state_dict().items()})
+        with torch.no_grad():
+            ref = oracle(twin, xc, sep).float()
+            before = B.launch_count()
+            y = mg(xd)
+            assert B.launch_count() - before <= 3          # (re-pack after a change) + the fused kernel
+            y2 = mg(xd)                                    # second call: the record is reused
+        assert torch.equal(y, y2)
+        err = O.compare4d(ref, y.float().cpu())
+        assert err < 1e-3, err
+
+    check(x, xg, False)
+    mg.d_conv.weight.data = (torch.randn(N, C * M, 1, 1, generator=g) * 0.05).bfloat16().cuda()      # write-back style assignment
+    check(x, xg, False)
+    mg.s_conv.weight.data = (torch.randn(C * M, 1, d, d, generator=g) * 0.3).bfloat16().cuda()
+    check(x, xg, False)
+    mg.d_conv.bias.data.mul_(3.0)                       # in place through .data: no version bump, the documented case for invalidate()
+    _ops.invalidate(mg)
+    check(x, xg, False)
+    x5 = torch.randn(5, C, H + 1, H, generator=g).bfloat16()                                          # another input shape
+    check(x5, x5.cuda().contiguous(memory_format=torch.channels_last), False)
+    check(x, xg, False)
+    mg.decomp()                                         # s_conv becomes a SeparableConv
+    check(x, xg, True)
+    mg.load_state_dict({k: (v * 0.5 if k == "d_conv.weight" else v) for k, v in mg.state_dict().items()})
+    check(x, xg, True)

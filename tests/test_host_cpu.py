@@ -244,3 +244,72 @@ def test_synthetic_loader_and_lr_schedule():
     assert _schedule(ArgTable(DEFAULT_SCHED_ARGS), 1e-3)(7) == 1e-3
     cos = _schedule(ArgTable(DEFAULT_SCHED_ARGS, dict(sched='cosine', epochs=10, min_lr=1e-5)), 1e-3)
     assert abs(cos(0) - 1e-3) < 1e-12 and abs(cos(10) - 1e-5) < 1e-12 and cos(5) < cos(1)
+
+
+def test_lowrank1_plan_record_host_logic(monkeypatch):
+    """Host logic of `LowRankExpConvV1._fused` without a GPU: the kernel entry points are replaced by counters, the layer and its
+    input stay on the CPU.  The per-layer record must reuse the packed operands call after call, pick the smallest basis instance
+    whose chunks divide C*M, and re-plan after `.weight.data = ...`, `decomp()`, `_ops.invalidate` and a new input shape — and only then."""
+    import torch
+    from approx import backend as B
+    from approx.layers import LowRankExpConvV1, _ops
+    calls = {"pack_s": 0, "pack_d": 0, "supported": [], "fused": []}
+
+    def pack_s(s_conv, M, m_pad=None):
+        calls["pack_s"] += 1
+        return torch.zeros(1)
+
+    def pack_d(w, C, M, m_pad):
+        calls["pack_d"] += 1
+        return torch.zeros(1)
+
+    def supported(Bn, H, W, C, N, M, d, sep):
+        calls["supported"].append(M)
+        return True
+
+    def fused(x, sp, dp, bias, M, d, sep):
+        calls["fused"].append((M, d, sep))
+        return x
+    monkeypatch.setattr(B, "lowrank1_pack_s", pack_s)
+    monkeypatch.setattr(B, "lowrank1_pack_d", pack_d)
+    monkeypatch.setattr(B, "lowrank1_fused_supported", supported)
+    monkeypatch.setattr(B, "lowrank1_fused", fused)
+    torch.manual_seed(0)
+    layer = LowRankExpConvV1(64, 32, 3, 1, 1, num_base=3).bfloat16().eval()
+    x = torch.zeros(2, 5, 5, 64, dtype=torch.bfloat16)                     # NHWC, as forward_nhwc receives it
+
+    def run(n=3, inp=x):
+        for _ in range(n):
+            assert layer._fused(inp) is inp
+    run()
+    assert (calls["pack_s"], calls["pack_d"]) == (1, 1) and calls["supported"] == [4]      # 64*2 % 64 == 0 but 2 < 3 bases: instance 4
+    assert calls["fused"] == [(4, 3, False)] * 3
+    layer.d_conv.weight.data = layer.d_conv.weight.data.clone()                             # the reference's write-back style
+    run()
+    assert (calls["pack_s"], calls["pack_d"]) == (1, 2)                                     # only d_conv's pack is rebuilt
+    layer.s_conv.bias.data.zero_()                                                          # in place through .data: invisible ...
+    run()
+    assert (calls["pack_s"], calls["pack_d"]) == (1, 2)
+    _ops.invalidate(layer)                                                                  # ... until invalidate()
+    run()
+    assert (calls["pack_s"], calls["pack_d"]) == (2, 3)
+    run(inp=torch.zeros(3, 5, 5, 64, dtype=torch.bfloat16))                                 # new shape: re-plan, packs reused
+    assert (calls["pack_s"], calls["pack_d"]) == (2, 3) and calls["supported"] == [4, 4, 4, 4]      # first call, write-back, invalidate, new shape
+    assert layer._fused(x.float()) is None and layer._fused(x.float()) is None              # fp32 input: not this kernel, decided once
+    assert layer._fused(x[:, :, ::2]) is None                                               # strided view: not this kernel
+    # decomp() swaps s_conv for a SeparableConv (needs the device SVD: stand in for it here)
+    from approx.layers.low_rank_conv import SeparableConv
+    layer.s_conv = SeparableConv(64, 3, (3, 3), (1, 1), (1, 1)).bfloat16()
+    n_fused = len(calls["fused"])
+    run()
+    assert calls["pack_s"] == 3 and calls["fused"][n_fused:] == [(4, 3, True)] * 3
+    # smallest instance: 2 bases on a 32-channel-multiple layer, 16 for 9..16, none above
+    for M, want in ((2, 2), (5, 8), (9, 16), (16, 16), (17, None)):
+        lay = LowRankExpConvV1(64, 32, 3, 1, 1, num_base=M).bfloat16().eval()
+        calls["fused"].clear()
+        out = lay._fused(x)
+        assert (out is None and want is None) or calls["fused"] == [(want, 3, False)], (M, want, calls["fused"])
+    lay = LowRankExpConvV1(16, 32, 3, 1, 1, num_base=2).bfloat16().eval()                     # 16*2 = 32 wide channels: instance 4 (64)
+    calls["fused"].clear()
+    lay._fused(torch.zeros(2, 5, 5, 16, dtype=torch.bfloat16))
+    assert calls["fused"] == [(4, 3, False)]

@@ -103,7 +103,7 @@ def empty_batch_safe(forward):
     import functools
 
     @functools.wraps(forward)
-    def wrapper(self, x, *args, **kwargs):
+    def wrapper(self, x=None, *args, **kwargs):              # (x may arrive by keyword)
         if isinstance(x, torch.Tensor) and x.dim() == 4 and x.shape[0] == 0 and min(x.shape[1:]) > 0:
             check_input(x)
             with torch.no_grad():

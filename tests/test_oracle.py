@@ -167,3 +167,47 @@ def test_golden_bf16_oracle_mode(golden):
     y = O.lowrank2_forward(bf(g["v2_x"]), bf(g["v2_v_conv.weight"]), bf(g["v2_h_conv.weight"]),
                            bf(g["v2_h_conv.bias"]), (1, 1), (1, 1))
     assert O.compare4d(T(g["v2_y"]), y.float()) < 1e-3
+
+
+def _svd_start(W, M):
+    """The reference's 'svd' starting point (core/low_rank_exp.py:110-120)."""
+    u, s, vh = np.linalg.svd(W, full_matrices=False)
+    k = min(M, s.shape[0])
+    A0, B0 = np.zeros((W.shape[0], M)), np.zeros((M, W.shape[1]))
+    A0[:, :k] = u[:, :k] * np.sqrt(s[:k])
+    B0[:k] = vh[:k] * np.sqrt(s[:k])[:, None]
+    return A0, B0
+
+
+def test_alternating_fit_steps_satisfy_the_optimality_conditions_of_the_cvxpy_programs():
+    """The reference solves `min_B sum_r ||W_r - A_r B||_2 + lmda sum_m ||B_m||_*` and `min_A ...` with cvxpy
+    (core/low_rank_exp.py:126-135, 160-176), which cannot run here.  The oracle's two steps are pinned to those convex programs
+    themselves: after a B-step (run to convergence) the bases satisfy the subgradient optimality conditions (nuclear-norm subdifferential)
+    to 1e-9, after an
+    A-step every row is a least-squares point — so each step returns an optimum of the program cvxpy is handed, whatever solver
+    finds it.  Also: the objective never increases along the trace, and a larger lambda gives bases of lower rank."""
+    rng = np.random.default_rng(0)
+    for d, M, R in ((3, 4, 200), (5, 8, 300), (3, 6, 120)):
+        W = rng.standard_normal((R, d * d))
+        A0, B0 = _svd_start(W, M)
+        ranks = []
+        for lmda in (0.05, 1.0, 5.0):
+            # one alternation, stopped after its B-step (epsilon = inf) ...
+            _, B1, tr = O.lowrank1_alt_fit_np(W, A0, B0, [lmda], 1, np.inf, d, inner=2000)
+            res_B, _ = O.lowrank1_alt_kkt_residual(W, A0, B1, lmda, d)
+            assert res_B < 1e-9, (d, M, lmda, res_B)
+            assert tr[0] <= O.lowrank1_alt_objective(W, A0, B0, lmda, d) + 1e-9 and tr[1] <= tr[0] + 1e-9
+            # ... and the pair after the A-step
+            A1, B1b, _ = O.lowrank1_alt_fit_np(W, A0, B0, [lmda], 1, np.inf, d, inner=2000)
+            assert np.array_equal(B1, B1b)
+            _, res_A = O.lowrank1_alt_kkt_residual(W, A1, B1, lmda, d)
+            assert res_A < 1e-8, (d, M, lmda, res_A)
+            # several alternations: monotone objective
+            _, B5, tr5 = O.lowrank1_alt_fit_np(W, A0, B0, [lmda], 5, 0.0, d)
+            assert all(b <= a + 1e-8 for a, b in zip(tr5, tr5[1:])), tr5
+            ranks.append(sum(int((np.linalg.svd(B5[m].reshape(d, d), compute_uv=False) > 1e-8).sum()) for m in range(M)))
+        assert ranks[0] >= ranks[1] >= ranks[2] and ranks[2] < ranks[0], ranks
+    # a perturbed optimum is detected
+    _, B1, _ = O.lowrank1_alt_fit_np(W, A0, B0, [1.0], 1, np.inf, d, inner=2000)
+    bad, _ = O.lowrank1_alt_kkt_residual(W, A0, B1 + 1e-3 * rng.standard_normal(B1.shape), 1.0, d)
+    assert bad > 1e-4

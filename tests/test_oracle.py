@@ -161,6 +161,28 @@ def test_lowrank2_svd_fit_full_rank_is_exact():
     assert O.compare4d(F.conv2d(x, W, b, 1, 1), y) < TOL
 
 
+def test_lowrank2_svd_fit_attains_the_eckart_young_optimum():
+    """True scheme 2 is absent from the reference, so its fit has no reference output to match; it is pinned to the optimum of the
+    problem instead (Jaderberg et al. 2014, section 3.2: min ||W - sum_k v_k * h_k||_F over K separable terms).  The effective d x d
+    filters of the fitted pair, W~[n,c,i,j] = sum_k v[k,c,i] h[n,k,j], miss W by exactly the discarded singular values of the
+    (C d) x (d N) reshaping (Eckart-Young), no rank-K pair of factors does better (random perturbations only increase the error),
+    and the two-conv forward equals a dense conv with W~."""
+    torch.manual_seed(3)
+    N, C, d, K = 10, 6, 3, 7
+    W = torch.randn(N, C, d, d)
+    v_w, h_w = O.lowrank2_svd_fit(W, K)
+    Wt = torch.einsum("kci,nkj->ncij", v_w[..., 0].double(), h_w[:, :, 0, :].double())
+    s = torch.linalg.svdvals(W.permute(1, 2, 3, 0).reshape(C * d, d * N).double())
+    err = (W.double() - Wt).norm()
+    assert abs(err - s[K:].norm()) < 1e-5 * s.norm(), (float(err), float(s[K:].norm()))
+    for t in range(20):
+        dv, dh = 1e-2 * torch.randn_like(v_w), 1e-2 * torch.randn_like(h_w)
+        Wp = torch.einsum("kci,nkj->ncij", (v_w + dv)[..., 0].double(), (h_w + dh)[:, :, 0, :].double())
+        assert (W.double() - Wp).norm() >= err - 1e-9
+    x = torch.randn(2, C, 9, 8); b = torch.randn(N)
+    assert O.compare4d(F.conv2d(x, Wt.float(), b, 1, 1), O.lowrank2_forward(x, v_w, h_w, b, (1, 1), (1, 1))) < TOL
+
+
 def test_golden_bf16_oracle_mode(golden):
     g = golden("bf16")
     bf = lambda a: T(a).to(torch.bfloat16)

@@ -313,3 +313,35 @@ def test_lowrank1_plan_record_host_logic(monkeypatch):
     calls["fused"].clear()
     lay._fused(torch.zeros(2, 5, 5, 16, dtype=torch.bfloat16))
     assert calls["fused"] == [(4, 3, False)]
+
+
+def test_empty_batch_wrapper_host_logic():
+    """`_ops.empty_batch_safe` without a GPU: a batch of zero images is answered from one zero image pushed through the wrapped
+    forward (shape and dtype of the result, no gradient graph), everything else — positional or keyword `x`, a zero-sized H —
+    reaches the wrapped forward untouched."""
+    from approx.layers import _ops
+    seen = []
+
+    class Layer(nn.Module):
+        @_ops.empty_batch_safe
+        def forward(self, x, scale=1):
+            seen.append(tuple(x.shape))
+            return x[:, :1, ::2, ::2].repeat(1, 5, 1, 1) * scale
+
+    layer = Layer()
+    import approx.backend as B
+    orig = B.require_cuda
+    B.require_cuda = lambda *a: None                      # the wrapper validates the empty input like any other
+    try:
+        y = layer(torch.zeros(0, 3, 8, 6))
+        assert y.shape == (0, 5, 4, 3) and seen == [(1, 3, 8, 6)] and not y.requires_grad
+        y = layer(torch.ones(2, 3, 8, 6), scale=2)
+        assert y.shape == (2, 5, 4, 3) and float(y.max()) == 2.0 and seen[-1] == (2, 3, 8, 6)
+        assert layer(x=torch.ones(1, 3, 4, 4)).shape == (1, 5, 2, 2)
+        layer(torch.zeros(0, 3, 0, 6))                    # no image to imitate: handed through as it is
+        assert seen[-1] == (0, 3, 0, 6)
+        with pytest.raises(ValueError):
+            _ops.check_input(torch.zeros(0, 3, 8))
+    finally:
+        B.require_cuda = orig
+    assert layer.forward.__name__ == "forward"
